@@ -1,0 +1,170 @@
+/*
+ * kvc_b200.h — C ABI of libkvc_b200.so: the B200-native (sm_100a) prefill KV-compression hot path.
+ *
+ * This is the drop-in boundary for the path that the reference (assassin808/KVCache-Factory)
+ * implements as a chain of PyTorch ops in pyramidkv/pyramidkv_utils.py plus one pybind11 CUDA
+ * function in csrc/csrc/cuda_api.cu.  Every entry point takes plain pointers, sizes and element
+ * strides (no torch types), returns an int status and launches on the caller's stream.
+ *
+ *   status == 0            ok (work is enqueued on `stream`; nothing is synchronised)
+ *   status  < 0            KVC_ERR_* argument / capability error, message via kvc_last_error()
+ *   status  > 0            a cudaError_t raised by a launch or an API call
+ *
+ * Conventions
+ *   - All tensor pointers are DEVICE pointers unless the name ends in `_host`.
+ *   - Q is logical [B,Hq,L,d], K and V are logical [B,Hkv,L,d] (un-repeated GQA layout; pass
+ *     Hkv == Hq for the reference's repeat_kv-expanded layout).  The last dimension must be
+ *     contiguous; the other three are described by ELEMENT strides (sb, sh, sl), because HF hands
+ *     query_states over as a transposed view.
+ *   - dtype: KVC_BF16 or KVC_FP16 (the reference kernel's FP16_SWITCH, csrc/static_switch.h:3-12).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - Workspaces are caller-allocated device memory; size them with the *_workspace_bytes calls.
+ *
+ * Reference interface each function replaces is cited as path:line under /root/reference.
+ */
+#ifndef KVC_B200_H_
+#define KVC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KVC_ABI_VERSION 1
+
+enum { KVC_BF16 = 0, KVC_FP16 = 1 };
+enum { KVC_POOL_NONE = 0, KVC_POOL_AVG = 1, KVC_POOL_MAX = 2 };
+enum { KVC_REDUCE_SUM = 0, KVC_REDUCE_MEAN = 1 };
+/* scoring implementation: AUTO picks the tcgen05/TMA kernel when the shape allows it */
+enum { KVC_IMPL_AUTO = 0, KVC_IMPL_MMA_SYNC = 1, KVC_IMPL_TCGEN05 = 2 };
+
+enum {
+  KVC_OK = 0,
+  KVC_ERR_ARG = -1,         /* malformed argument (null pointer, non-positive size, bad enum)      */
+  KVC_ERR_UNSUPPORTED = -2, /* shape/dtype outside what the sm_100a kernels implement              */
+  KVC_ERR_WORKSPACE = -3,   /* workspace too small                                                 */
+  KVC_ERR_DEVICE = -4       /* not an sm_100 device / no CUDA device                               */
+};
+
+/* ABI version of the loaded library (== KVC_ABI_VERSION it was built with). */
+int kvc_version(void);
+/* Thread-local description of the last non-zero status returned on this thread. */
+const char* kvc_last_error(void);
+/* Number of SMs of the current device (grids are sized in multiples of it). */
+int kvc_sm_count(int* out_sms);
+
+/* ------------------------------------------------------------------------------------------------
+ * Window scoring — replaces the matmul / div / mask / softmax / sum chain of
+ *   SnapKVCluster.update_kv      pyramidkv/pyramidkv_utils.py:317-327
+ *   PyramidKVCluster.update_kv   pyramidkv/pyramidkv_utils.py:221-232, 253-260
+ *   AdaKVCluster.calcul_attn_sore pyramidkv/pyramidkv_utils.py:649-661 (reduce = MEAN)
+ * and folds repeat_kv (pyramidkv_utils.py:108-117) into the kernel: each KV head is read once for
+ * its Hq/Hkv query heads.
+ *
+ * out_scores[b,h,j] (dtype, contiguous [B,Hq,L-w]) = model-dtype rounding of
+ *   sum|mean over the last w query rows i of  round( softmax_j( round(round(q_i.k_j)/sqrt(d)) + causal_ww ) )
+ * with the reference's rounding points (GEMM result, scaled logits, probabilities and the
+ * reduction are each rounded to `dtype`; softmax itself is fp32).
+ * ---------------------------------------------------------------------------------------------- */
+size_t kvc_window_scores_workspace_bytes(int B, int Hq, int Hkv, int L, int d, int w);
+int kvc_window_scores(const void* q, int64_t q_sb, int64_t q_sh, int64_t q_sl,
+                      const void* k, int64_t k_sb, int64_t k_sh, int64_t k_sl,
+                      int B, int Hq, int Hkv, int L, int d, int w,
+                      int dtype, int reduce, void* out_scores,
+                      void* workspace, size_t workspace_bytes, int impl, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * H2O scoring — replaces H2OKVCluster.update_kv pyramidkv/pyramidkv_utils.py:544-554: ALL L query
+ * rows score every key (non-causal except the bottom-right w x w block), column-summed.  The
+ * [B,H,L,L] matrix is never materialised.
+ * ---------------------------------------------------------------------------------------------- */
+size_t kvc_h2o_scores_workspace_bytes(int B, int Hq, int Hkv, int L, int d, int w);
+int kvc_h2o_scores(const void* q, int64_t q_sb, int64_t q_sh, int64_t q_sl,
+                   const void* k, int64_t k_sb, int64_t k_sh, int64_t k_sl,
+                   int B, int Hq, int Hkv, int L, int d, int w,
+                   int dtype, void* out_scores,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Pool + top-k — replaces F.avg_pool1d / F.max_pool1d (stride 1, padding kernel/2) followed by
+ * Tensor.topk(k).indices: pyramidkv/pyramidkv_utils.py:328-334 (SnapKV), :233-239 / :261-270
+ * (PyramidKV), :562-563 (H2O, pool = NONE), and the per-head sort prefix of AdaKV (:706, :734).
+ *
+ * scores: [rows, n] dtype contiguous.  For every row the k largest pooled values are selected;
+ * out_idx[row, 0..k) lists their positions ordered by DESCENDING pooled value (torch.topk
+ * sorted=True), equal values by ascending position (torch leaves tie order unspecified).
+ *   k_per_row == NULL : every row selects `k` entries, out_idx row stride = idx_stride (>= k)
+ *   k_per_row != NULL : device int32[rows]; row r selects k_per_row[r] <= k_max = k entries
+ * out_pooled (optional, may be NULL): [rows, n] dtype, the pooled scores the selection was made on.
+ * out_sums (optional, may be NULL): float[rows,2] = {fp32 sum of the selected values in output
+ * order, fp32 sum of all pooled values} (AdaKV ratio normalisation, pyramidkv_utils.py:709-711).
+ * ---------------------------------------------------------------------------------------------- */
+size_t kvc_pool_topk_workspace_bytes(int rows, int n, int k);
+int kvc_pool_topk(const void* scores, int rows, int n, int dtype, int kernel_size, int pool,
+                  int k, const int32_t* k_per_row, int32_t* out_idx, int64_t idx_stride,
+                  void* out_pooled, float* out_sums,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Dense gather/compact — replaces gather(dim=2, idx) + cat([.., window]) for K and V:
+ * pyramidkv/pyramidkv_utils.py:341-346 (SnapKV), :245-250 / :277-282 (PyramidKV), :569-574 (H2O),
+ * :607-619 (StreamingLLM: pass idx == NULL for idx = arange(n_sel), no index tensor is built).
+ *
+ * out_k/out_v: contiguous [B,Hq,n_sel+w,d].  Row r < n_sel of head h copies K[b, h/(Hq/Hkv),
+ * idx[b,h,r], :]; rows n_sel.. copy the last w rows.  idx: int32 [B,Hq,n_sel], values in [0,L-w).
+ * Bytes move untouched (bit-exact); elem_bytes in {2,4}.
+ * ---------------------------------------------------------------------------------------------- */
+int kvc_gather_dense(const void* k, int64_t k_sb, int64_t k_sh, int64_t k_sl,
+                     const void* v, int64_t v_sb, int64_t v_sh, int64_t v_sl,
+                     const int32_t* idx, int B, int Hq, int Hkv, int L, int d, int n_sel, int w,
+                     int elem_bytes, void* out_k, void* out_v, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Varlen (flattened) gather — replaces the per-head Python loop of AdaKVCluster.update_kv
+ * pyramidkv/pyramidkv_utils.py:733-755: head h writes cap[h] selected rows then the w window rows
+ * at row offset cu_klen[h] of the flattened [sum_h(cap[h]+w), d] cache.  Batch is 1 (:724).
+ * idx: int32 [Hq, idx_stride]; cap, cu_klen: device int32 [Hq], [Hq+1].
+ * ---------------------------------------------------------------------------------------------- */
+int kvc_gather_varlen(const void* k, int64_t k_sh, int64_t k_sl,
+                      const void* v, int64_t v_sh, int64_t v_sl,
+                      const int32_t* idx, int64_t idx_stride, const int32_t* cap,
+                      const int32_t* cu_klen, int Hq, int Hkv, int L, int d, int w, int max_cap,
+                      int elem_bytes, void* out_k, void* out_v, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * AdaKV head-adaptive allocation — replaces pyramidkv/pyramidkv_utils.py:706-719 + init_metadata
+ * (:682-698): ratio-normalise each head's pooled scores, take the global top-(H*base) over all
+ * heads, count winners per head and apply the floor:
+ *   cap[h] = round_half_even(count[h] * (1 - floor_ratio) + int(base * floor_ratio))
+ * pooled: [H, n] dtype; sums: float[H,2] from kvc_pool_topk(k = base).  Outputs (device int32):
+ * cap[H], head_lens[H] = cap + w, cu_klen[H+1] (exclusive prefix + total).
+ * counts_inout (optional): int32[H] raw winner counts; with n_ranks > 1 the caller all-reduces the
+ * two histograms between the phases (see kvcache_factory_b200/sharding.py), the single-GPU entry
+ * does everything in one call.
+ * ---------------------------------------------------------------------------------------------- */
+size_t kvc_adakv_allocate_workspace_bytes(int H, int n);
+int kvc_adakv_allocate(const void* pooled, const float* sums, int H, int n, int dtype,
+                       int base_capacity, float one_minus_floor, int floor_capacity, int normalize,
+                       int w, int32_t* out_cap, int32_t* out_head_lens, int32_t* out_cu_klen,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Flattened-cache append — replaces tiny_api_cuda.update_flatten_view
+ * csrc/csrc/cuda_api.cu:55-85 (kernel :11-53), called by DynamicCacheSplitHeadFlatten.update
+ * pyramidkv/pyramidkv_utils.py:66-67.
+ *
+ * dst: [total_rows + H, d]; src: [total_rows, d]; state: [H, d]; headlens int32[H];
+ * cu_headlens int32[H+1].  For head h: dst rows [cu[h]+h, cu[h]+h+headlens[h]) = src rows
+ * [cu[h], cu[h]+headlens[h]) and dst row cu[h+1]+h = state[h].  d*elem_bytes <= 256 as in the
+ * reference (cuda_api.cu:74 requires head_dim <= 128 of a 16-bit type).
+ * ---------------------------------------------------------------------------------------------- */
+int kvc_update_flatten_view(void* dst, const void* src, const void* state,
+                            const int32_t* headlens, const int32_t* cu_headlens,
+                            int H, int d, int elem_bytes, int64_t total_rows, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KVC_B200_H_ */

@@ -1,0 +1,289 @@
+"""ctypes binding of ``libkvc_b200.so`` (C ABI declared in ``include/kvc_b200.h``).
+
+PyTorch is used here for device memory, streams and nothing else: every function marshals
+``tensor.data_ptr()``, element strides and the current CUDA stream into the C ABI.  There is no CPU
+path and no alternative backend: if the library is missing or the tensors are not on a CUDA device
+the call raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p, POINTER
+
+import torch
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG_DIR, "libkvc_b200.so")
+
+KVC_BF16, KVC_FP16 = 0, 1
+POOL_NONE, POOL_AVG, POOL_MAX = 0, 1, 2
+REDUCE_SUM, REDUCE_MEAN = 0, 1
+IMPL_AUTO, IMPL_MMA_SYNC, IMPL_TCGEN05 = 0, 1, 2
+ABI_VERSION = 1
+
+_POOL = {None: POOL_NONE, "none": POOL_NONE, "avgpool": POOL_AVG, "maxpool": POOL_MAX}
+
+# name -> (restype, argtypes); mirrors include/kvc_b200.h one to one
+_i64, _p, _i = c_int64, c_void_p, c_int
+_SIGNATURES = {
+    "kvc_version": (c_int, []),
+    "kvc_last_error": (c_char_p, []),
+    "kvc_sm_count": (c_int, [POINTER(c_int)]),
+    "kvc_window_scores_workspace_bytes": (c_size_t, [_i] * 6),
+    "kvc_window_scores": (c_int, [_p, _i64, _i64, _i64, _p, _i64, _i64, _i64, _i, _i, _i, _i, _i, _i, _i, _i, _p,
+                                  _p, c_size_t, _i, _p]),
+    "kvc_h2o_scores_workspace_bytes": (c_size_t, [_i] * 6),
+    "kvc_h2o_scores": (c_int, [_p, _i64, _i64, _i64, _p, _i64, _i64, _i64, _i, _i, _i, _i, _i, _i, _i, _p, _p,
+                               c_size_t, _p]),
+    "kvc_pool_topk_workspace_bytes": (c_size_t, [_i] * 3),
+    "kvc_pool_topk": (c_int, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _i64, _p, _p, _p, c_size_t, _p]),
+    "kvc_gather_dense": (c_int, [_p, _i64, _i64, _i64, _p, _i64, _i64, _i64, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p,
+                                 _p, _p]),
+    "kvc_gather_varlen": (c_int, [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p,
+                                  _p, _p]),
+    "kvc_adakv_allocate_workspace_bytes": (c_size_t, [_i] * 2),
+    "kvc_adakv_allocate": (c_int, [_p, _p, _i, _i, _i, _i, c_float, _i, _i, _i, _p, _p, _p, _p, c_size_t, _p]),
+    "kvc_update_flatten_view": (c_int, [_p, _p, _p, _p, _p, _i, _i, _i, _i64, _p]),
+}
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+
+
+class KvcError(RuntimeError):
+    """Non-zero status from libkvc_b200 (negative: argument/capability, positive: cudaError_t)."""
+
+    def __init__(self, fn: str, status: int, message: str):
+        super().__init__(f"{fn} failed with status {status}: {message}")
+        self.status = status
+
+
+def lib() -> ctypes.CDLL:
+    """Load the CUDA library (once).  Raises if it has not been built: there is no fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `make -C kvcache_factory_b200/csrc` or "
+                "`python -c 'import __graft_entry__ as g; g.build()'`. kvcache_factory_b200 has no CPU or "
+                "PyTorch fallback for the compression path.")
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(handle, name)  # AttributeError here = header/library mismatch
+            fn.restype, fn.argtypes = res, args
+        if handle.kvc_version() != ABI_VERSION:
+            raise RuntimeError(f"libkvc_b200 ABI {handle.kvc_version()} != binding ABI {ABI_VERSION}")
+        _lib = handle
+    return _lib
+
+
+def _check(fn: str, status: int) -> None:
+    if status != 0:
+        msg = lib().kvc_last_error()
+        raise KvcError(fn, status, msg.decode() if msg else "")
+
+
+def dtype_code(dtype: torch.dtype) -> int:
+    if dtype == torch.bfloat16:
+        return KVC_BF16
+    if dtype == torch.float16:
+        return KVC_FP16
+    raise TypeError(f"kvcache_factory_b200 kernels take bf16 or fp16 tensors, got {dtype} "
+                    "(the reference's native kernel has the same restriction, csrc/static_switch.h:3-12)")
+
+
+def pool_code(pooling) -> int:
+    if pooling not in _POOL:
+        raise ValueError("Pooling method not supported")  # pyramidkv_utils.py:237,333
+    return _POOL[pooling]
+
+
+def _require_cuda(*tensors: torch.Tensor) -> torch.device:
+    dev = tensors[0].device
+    for t in tensors:
+        if t.device.type != "cuda":
+            raise RuntimeError("kvcache_factory_b200 runs on CUDA tensors only (no CPU fallback); got a tensor on "
+                               f"{t.device}")
+        if t.device != dev:
+            raise RuntimeError(f"tensors on different devices: {dev} vs {t.device}")
+    return dev
+
+
+def _stream(dev: torch.device) -> int:
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def _rowmajor_last(t: torch.Tensor, align_elems: int) -> torch.Tensor:
+    """Kernels need a unit-stride last dim and (for K/V) 16-byte aligned rows; HF tensors have both.
+    Anything else is repacked once on the device (a copy kernel, not a compute fallback)."""
+    ok = t.stride(-1) == 1 and all(s % align_elems == 0 for s in t.stride()[:-1]) \
+        and t.data_ptr() % (2 * align_elems) == 0
+    return t if ok else t.contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# op wrappers
+# ------------------------------------------------------------------------------------------------
+def window_scores(query_states: torch.Tensor, key_states: torch.Tensor, window_size: int,
+                  reduce: str = "sum", impl: int = IMPL_AUTO) -> torch.Tensor:
+    """[B,Hq,L-w] scores of every non-window key under the last ``window_size`` queries."""
+    dev = _require_cuda(query_states, key_states)
+    B, Hq, L, d = query_states.shape
+    Hkv = key_states.shape[1]
+    code = dtype_code(key_states.dtype)
+    if query_states.dtype != key_states.dtype:
+        raise TypeError("query and key dtypes differ")
+    q = _rowmajor_last(query_states, 2)
+    k = _rowmajor_last(key_states, 8)
+    out = torch.empty((B, Hq, L - window_size), dtype=key_states.dtype, device=dev)
+    with torch.cuda.device(dev):
+        ws_bytes = lib().kvc_window_scores_workspace_bytes(B, Hq, Hkv, L, d, window_size)
+        ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=dev)
+        _check("kvc_window_scores", lib().kvc_window_scores(
+            q.data_ptr(), q.stride(0), q.stride(1), q.stride(2),
+            k.data_ptr(), k.stride(0), k.stride(1), k.stride(2),
+            B, Hq, Hkv, L, d, window_size, code, REDUCE_MEAN if reduce == "mean" else REDUCE_SUM,
+            out.data_ptr(), ws.data_ptr(), ws.numel(), impl, _stream(dev)))
+    return out
+
+
+def h2o_scores(query_states: torch.Tensor, key_states: torch.Tensor, window_size: int) -> torch.Tensor:
+    dev = _require_cuda(query_states, key_states)
+    B, Hq, L, d = query_states.shape
+    Hkv = key_states.shape[1]
+    code = dtype_code(key_states.dtype)
+    q = _rowmajor_last(query_states, 8)
+    k = _rowmajor_last(key_states, 8)
+    out = torch.empty((B, Hq, L - window_size), dtype=key_states.dtype, device=dev)
+    with torch.cuda.device(dev):
+        ws_bytes = lib().kvc_h2o_scores_workspace_bytes(B, Hq, Hkv, L, d, window_size)
+        ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=dev)
+        _check("kvc_h2o_scores", lib().kvc_h2o_scores(
+            q.data_ptr(), q.stride(0), q.stride(1), q.stride(2),
+            k.data_ptr(), k.stride(0), k.stride(1), k.stride(2),
+            B, Hq, Hkv, L, d, window_size, code, out.data_ptr(), ws.data_ptr(), ws.numel(), _stream(dev)))
+    return out
+
+
+def pool_topk(scores: torch.Tensor, kernel_size: int, pooling, k: int, k_per_row: torch.Tensor = None,
+              want_pooled: bool = False, want_sums: bool = False):
+    """Pool + per-row top-k.  Returns (idx int32 [..., k], pooled or None, sums float[rows,2] or None)."""
+    dev = _require_cuda(scores)
+    code = dtype_code(scores.dtype)
+    pcode = pool_code(pooling)
+    lead, n = scores.shape[:-1], scores.shape[-1]
+    rows = 1
+    for s in lead:
+        rows *= s
+    scores = scores.contiguous()
+    idx = torch.empty((*lead, k), dtype=torch.int32, device=dev)
+    pooled = torch.empty_like(scores) if want_pooled else None
+    sums = torch.empty((rows, 2), dtype=torch.float32, device=dev) if want_sums else None
+    if k_per_row is not None:
+        if k_per_row.dtype != torch.int32 or k_per_row.numel() != rows:
+            raise TypeError("k_per_row must be an int32 tensor with one entry per row")
+        _require_cuda(scores, k_per_row)
+    with torch.cuda.device(dev):
+        ws_bytes = lib().kvc_pool_topk_workspace_bytes(rows, n, k)
+        ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=dev)
+        _check("kvc_pool_topk", lib().kvc_pool_topk(
+            scores.data_ptr(), rows, n, code, kernel_size, pcode, k,
+            k_per_row.data_ptr() if k_per_row is not None else None, idx.data_ptr(), k,
+            pooled.data_ptr() if pooled is not None else None, sums.data_ptr() if sums is not None else None,
+            ws.data_ptr(), ws.numel(), _stream(dev)))
+    return idx, pooled, sums
+
+
+def gather_dense(key_states: torch.Tensor, value_states: torch.Tensor, idx, num_heads: int, n_sel: int,
+                 window_size: int):
+    """Compressed (K', V') [B,Hq,n_sel+w,d]; ``idx=None`` keeps the first n_sel rows (StreamingLLM)."""
+    dev = _require_cuda(key_states, value_states)
+    B, Hkv, L, d = key_states.shape
+    if value_states.shape != key_states.shape or value_states.dtype != key_states.dtype:
+        raise ValueError("key_states and value_states must have the same shape and dtype")
+    e = key_states.element_size()
+    k = _rowmajor_last(key_states, 16 // e)
+    v = _rowmajor_last(value_states, 16 // e)
+    if idx is not None:
+        _require_cuda(key_states, idx)
+        if idx.dtype != torch.int32 or not idx.is_contiguous():
+            raise TypeError("idx must be a contiguous int32 tensor")
+    out_k = torch.empty((B, num_heads, n_sel + window_size, d), dtype=k.dtype, device=dev)
+    out_v = torch.empty_like(out_k)
+    with torch.cuda.device(dev):
+        _check("kvc_gather_dense", lib().kvc_gather_dense(
+            k.data_ptr(), k.stride(0), k.stride(1), k.stride(2),
+            v.data_ptr(), v.stride(0), v.stride(1), v.stride(2),
+            idx.data_ptr() if idx is not None else None, B, num_heads, Hkv, L, d, n_sel, window_size, e,
+            out_k.data_ptr(), out_v.data_ptr(), _stream(dev)))
+    return out_k, out_v
+
+
+def gather_varlen(key_states, value_states, idx, cap, cu_klen, num_heads: int, window_size: int, max_cap: int,
+                  total_rows: int):
+    """Flattened (K', V') [total_rows, d]: head h owns rows [cu_klen[h], cu_klen[h+1])."""
+    dev = _require_cuda(key_states, value_states, idx, cap, cu_klen)
+    B, Hkv, L, d = key_states.shape
+    assert B == 1                                                   # pyramidkv_utils.py:724
+    e = key_states.element_size()
+    k = _rowmajor_last(key_states, 16 // e)
+    v = _rowmajor_last(value_states, 16 // e)
+    out_k = torch.empty((total_rows, d), dtype=k.dtype, device=dev)
+    out_v = torch.empty_like(out_k)
+    with torch.cuda.device(dev):
+        _check("kvc_gather_varlen", lib().kvc_gather_varlen(
+            k.data_ptr(), k.stride(1), k.stride(2), v.data_ptr(), v.stride(1), v.stride(2),
+            idx.data_ptr(), idx.stride(-2), cap.data_ptr(), cu_klen.data_ptr(), num_heads, Hkv, L, d, window_size,
+            max_cap, e, out_k.data_ptr(), out_v.data_ptr(), _stream(dev)))
+    return out_k, out_v
+
+
+def adakv_allocate(pooled: torch.Tensor, sums: torch.Tensor, base_capacity: int, floor_ratio: float,
+                   normalize: bool, window_size: int):
+    """Device int32 tensors (cap[H], head_lens[H], cu_klen[H+1]) from pooled [H,n] scores."""
+    dev = _require_cuda(pooled, sums)
+    H, n = pooled.shape
+    code = dtype_code(pooled.dtype)
+    cap = torch.empty(H, dtype=torch.int32, device=dev)
+    head_lens = torch.empty(H, dtype=torch.int32, device=dev)
+    cu_klen = torch.empty(H + 1, dtype=torch.int32, device=dev)
+    # torch evaluates `counts * (1 - floor_ratio)` with the Python double rounded to fp32
+    one_minus_floor = float(torch.tensor(1 - floor_ratio, dtype=torch.float32))
+    with torch.cuda.device(dev):
+        ws_bytes = lib().kvc_adakv_allocate_workspace_bytes(H, n)
+        ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=dev)
+        _check("kvc_adakv_allocate", lib().kvc_adakv_allocate(
+            pooled.data_ptr(), sums.data_ptr(), H, n, code, base_capacity, one_minus_floor,
+            int(base_capacity * floor_ratio), int(bool(normalize)), window_size,
+            cap.data_ptr(), head_lens.data_ptr(), cu_klen.data_ptr(), ws.data_ptr(), ws.numel(), _stream(dev)))
+    return cap, head_lens, cu_klen
+
+
+def update_flatten_view(cache: torch.Tensor, state: torch.Tensor, headlens: torch.Tensor,
+                        cu_headlens: torch.Tensor) -> torch.Tensor:
+    """Drop-in for ``tiny_api_cuda.update_flatten_view`` (csrc/csrc/cuda_api.cu:55-85)."""
+    if headlens.dtype != torch.int32:
+        raise RuntimeError("expected headlens to be int32")          # cuda_api.cu:56
+    if cu_headlens.dtype != torch.int32:
+        raise RuntimeError("expected cu_dst_pos to be int32")        # cuda_api.cu:57
+    dev = _require_cuda(cache, state, headlens, cu_headlens)
+    dtype_code(cache.dtype)
+    total, d = cache.shape
+    H = headlens.shape[0]
+    if d > 128:
+        raise RuntimeError("num threads should larger than head dim")  # cuda_api.cu:74
+    cache = cache.contiguous()
+    state = state.contiguous()
+    out = torch.empty((total + H, d), dtype=cache.dtype, device=dev)
+    with torch.cuda.device(dev):
+        _check("kvc_update_flatten_view", lib().kvc_update_flatten_view(
+            out.data_ptr(), cache.data_ptr(), state.data_ptr(), headlens.data_ptr(), cu_headlens.data_ptr(),
+            H, d, cache.element_size(), total, _stream(dev)))
+    return out
+
+
+def sm_count() -> int:
+    n = c_int(0)
+    _check("kvc_sm_count", lib().kvc_sm_count(ctypes.byref(n)))
+    return n.value

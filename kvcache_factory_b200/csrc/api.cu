@@ -1,0 +1,215 @@
+// extern "C" surface of libkvc_b200.so (declared in include/kvc_b200.h): argument validation,
+// device check, dispatch to the sm_100a kernels.  No torch types cross this boundary.
+#include <mutex>
+
+#include "common.cuh"
+
+namespace kvc {
+
+// kernels implemented in the other translation units
+int gather_dense(const void*, int64_t, int64_t, int64_t, const void*, int64_t, int64_t, int64_t, const int32_t*, int,
+                 int, int, int, int, int, int, int, void*, void*, cudaStream_t);
+int gather_varlen(const void*, int64_t, int64_t, const void*, int64_t, int64_t, const int32_t*, int64_t,
+                  const int32_t*, const int32_t*, int, int, int, int, int, int, int, void*, void*, cudaStream_t);
+int update_flatten_view(void*, const void*, const void*, const int32_t*, const int32_t*, int, int, int, int64_t,
+                        cudaStream_t);
+size_t pool_topk_workspace_bytes(int rows, int n, int k);
+int pool_topk(const void*, int, int, int, int, int, int, const int32_t*, int32_t*, int64_t, void*, float*, void*,
+              size_t, cudaStream_t);
+size_t window_scores_mma_workspace_bytes(int B, int Hq, int Hkv, int L, int d, int w);
+int window_scores_mma(const void*, int64_t, int64_t, int64_t, const void*, int64_t, int64_t, int64_t, int, int, int,
+                      int, int, int, int, int, void*, void*, size_t, cudaStream_t);
+size_t window_scores_tc_workspace_bytes(int B, int Hq, int Hkv, int L, int d, int w);
+bool window_scores_tc_supported(int B, int Hq, int Hkv, int L, int d, int w);
+int window_scores_tc(const void*, int64_t, int64_t, int64_t, const void*, int64_t, int64_t, int64_t, int, int, int,
+                     int, int, int, int, int, void*, void*, size_t, cudaStream_t);
+size_t h2o_scores_workspace_bytes(int B, int Hq, int Hkv, int L, int d, int w);
+int h2o_scores(const void*, int64_t, int64_t, int64_t, const void*, int64_t, int64_t, int64_t, int, int, int, int,
+               int, int, int, void*, void*, size_t, cudaStream_t);
+size_t adakv_allocate_workspace_bytes(int H, int n);
+int adakv_allocate(const void*, const float*, int, int, int, int, float, int, int, int, int32_t*, int32_t*, int32_t*,
+                   void*, size_t, cudaStream_t);
+
+static thread_local char g_err[512] = "";
+char* last_error_buffer() { return g_err; }
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+// The library carries sm_100a SASS only: refuse anything else loudly instead of failing at launch.
+static int check_device() {
+  static int ok[64] = {0};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return fail(KVC_ERR_DEVICE, "no CUDA device: %s", cudaGetErrorString(e));
+  if (dev >= 0 && dev < 64 && ok[dev]) return 0;
+  int major = 0, minor = 0;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+  if (major != 10) return fail(KVC_ERR_DEVICE, "device %d is sm_%d%d; libkvc_b200 is built for sm_100a only", dev, major, minor);
+  if (dev >= 0 && dev < 64) ok[dev] = 1;
+  return 0;
+}
+
+static int check_shape(int B, int Hq, int Hkv, int L, int d, int w, int dtype) {
+  KVC_REQUIRE(B > 0 && Hq > 0 && Hkv > 0 && L > 0 && d > 0 && w > 0, KVC_ERR_ARG, "non-positive dimension");
+  KVC_REQUIRE(Hq % Hkv == 0, KVC_ERR_ARG, "Hq=%d is not a multiple of Hkv=%d", Hq, Hkv);
+  KVC_REQUIRE(w < L, KVC_ERR_ARG, "window %d must be smaller than the prompt length %d", w, L);
+  KVC_REQUIRE(dtype == KVC_BF16 || dtype == KVC_FP16, KVC_ERR_UNSUPPORTED,
+              "dtype %d: only bf16 and fp16 are implemented (as in the reference kernel)", dtype);
+  return 0;
+}
+
+}  // namespace kvc
+
+using namespace kvc;
+
+extern "C" {
+
+int kvc_version(void) { return KVC_ABI_VERSION; }
+const char* kvc_last_error(void) { return last_error_buffer(); }
+
+int kvc_sm_count(int* out_sms) {
+  KVC_REQUIRE(out_sms != nullptr, KVC_ERR_ARG, "out_sms is null");
+  if (int rc = check_device()) return rc;
+  *out_sms = sm_count();
+  return 0;
+}
+
+size_t kvc_window_scores_workspace_bytes(int B, int Hq, int Hkv, int L, int d, int w) {
+  if (B <= 0 || Hq <= 0 || Hkv <= 0 || L <= 0 || w <= 0 || Hq % Hkv) return 0;
+  size_t a = window_scores_mma_workspace_bytes(B, Hq, Hkv, L, d, w);
+  size_t b = window_scores_tc_workspace_bytes(B, Hq, Hkv, L, d, w);
+  return a > b ? a : b;
+}
+
+int kvc_window_scores(const void* q, int64_t q_sb, int64_t q_sh, int64_t q_sl, const void* k, int64_t k_sb,
+                      int64_t k_sh, int64_t k_sl, int B, int Hq, int Hkv, int L, int d, int w, int dtype, int reduce,
+                      void* out_scores, void* workspace, size_t workspace_bytes, int impl, void* stream) {
+  if (int rc = check_device()) return rc;
+  if (int rc = check_shape(B, Hq, Hkv, L, d, w, dtype)) return rc;
+  KVC_REQUIRE(q && k && out_scores && workspace, KVC_ERR_ARG, "null pointer argument");
+  KVC_REQUIRE(reduce == KVC_REDUCE_SUM || reduce == KVC_REDUCE_MEAN, KVC_ERR_ARG, "bad reduce %d", reduce);
+  KVC_REQUIRE(impl >= KVC_IMPL_AUTO && impl <= KVC_IMPL_TCGEN05, KVC_ERR_ARG, "bad impl %d", impl);
+  const bool tc_ok = window_scores_tc_supported(B, Hq, Hkv, L, d, w);
+  if (impl == KVC_IMPL_TCGEN05 && !tc_ok)
+    return fail(KVC_ERR_UNSUPPORTED, "tcgen05 scoring kernel does not cover this shape (Hq/Hkv=%d, w=%d, d=%d)",
+                Hq / Hkv, w, d);
+  if (impl == KVC_IMPL_TCGEN05 || (impl == KVC_IMPL_AUTO && tc_ok))
+    return window_scores_tc(q, q_sb, q_sh, q_sl, k, k_sb, k_sh, k_sl, B, Hq, Hkv, L, d, w, dtype, reduce, out_scores,
+                            workspace, workspace_bytes, (cudaStream_t)stream);
+  return window_scores_mma(q, q_sb, q_sh, q_sl, k, k_sb, k_sh, k_sl, B, Hq, Hkv, L, d, w, dtype, reduce, out_scores,
+                           workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+size_t kvc_h2o_scores_workspace_bytes(int B, int Hq, int Hkv, int L, int d, int w) {
+  if (B <= 0 || Hq <= 0 || Hkv <= 0 || L <= 0 || w <= 0 || Hq % Hkv) return 0;
+  return h2o_scores_workspace_bytes(B, Hq, Hkv, L, d, w);
+}
+
+int kvc_h2o_scores(const void* q, int64_t q_sb, int64_t q_sh, int64_t q_sl, const void* k, int64_t k_sb, int64_t k_sh,
+                   int64_t k_sl, int B, int Hq, int Hkv, int L, int d, int w, int dtype, void* out_scores,
+                   void* workspace, size_t workspace_bytes, void* stream) {
+  if (int rc = check_device()) return rc;
+  if (int rc = check_shape(B, Hq, Hkv, L, d, w, dtype)) return rc;
+  KVC_REQUIRE(q && k && out_scores && workspace, KVC_ERR_ARG, "null pointer argument");
+  return h2o_scores(q, q_sb, q_sh, q_sl, k, k_sb, k_sh, k_sl, B, Hq, Hkv, L, d, w, dtype, out_scores, workspace,
+                    workspace_bytes, (cudaStream_t)stream);
+}
+
+size_t kvc_pool_topk_workspace_bytes(int rows, int n, int k) {
+  if (rows <= 0 || n <= 0 || k < 0) return 0;
+  return pool_topk_workspace_bytes(rows, n, k);
+}
+
+int kvc_pool_topk(const void* scores, int rows, int n, int dtype, int kernel_size, int pool, int k,
+                  const int32_t* k_per_row, int32_t* out_idx, int64_t idx_stride, void* out_pooled, float* out_sums,
+                  void* workspace, size_t workspace_bytes, void* stream) {
+  if (int rc = check_device()) return rc;
+  KVC_REQUIRE(scores && workspace && (out_idx || k == 0), KVC_ERR_ARG, "null pointer argument");
+  KVC_REQUIRE(rows > 0 && n > 0, KVC_ERR_ARG, "rows=%d n=%d must be positive", rows, n);
+  KVC_REQUIRE(k >= 0 && k <= n, KVC_ERR_ARG, "k=%d outside [0, n=%d] (torch.topk raises for k > n)", k, n);
+  KVC_REQUIRE(idx_stride >= k, KVC_ERR_ARG, "idx_stride %lld < k %d", (long long)idx_stride, k);
+  KVC_REQUIRE(dtype == KVC_BF16 || dtype == KVC_FP16, KVC_ERR_UNSUPPORTED, "dtype %d", dtype);
+  KVC_REQUIRE(pool == KVC_POOL_NONE || pool == KVC_POOL_AVG || pool == KVC_POOL_MAX, KVC_ERR_ARG,
+              "Pooling method not supported (pool=%d)", pool);
+  KVC_REQUIRE(pool == KVC_POOL_NONE || (kernel_size >= 1 && (kernel_size & 1)), KVC_ERR_UNSUPPORTED,
+              "kernel_size %d: only odd kernels keep the sequence length (see DESIGN.md)", kernel_size);
+  return pool_topk(scores, rows, n, dtype, kernel_size, pool, k, k_per_row, out_idx, idx_stride, out_pooled, out_sums,
+                   workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int kvc_gather_dense(const void* k, int64_t k_sb, int64_t k_sh, int64_t k_sl, const void* v, int64_t v_sb,
+                     int64_t v_sh, int64_t v_sl, const int32_t* idx, int B, int Hq, int Hkv, int L, int d, int n_sel,
+                     int w, int elem_bytes, void* out_k, void* out_v, void* stream) {
+  if (int rc = check_device()) return rc;
+  KVC_REQUIRE(k && v && out_k && out_v, KVC_ERR_ARG, "null pointer argument");
+  KVC_REQUIRE(B > 0 && Hq > 0 && Hkv > 0 && Hq % Hkv == 0 && L > 0 && d > 0, KVC_ERR_ARG, "bad head geometry");
+  KVC_REQUIRE(w >= 0 && n_sel >= 0 && n_sel + w > 0 && n_sel <= L - w, KVC_ERR_ARG,
+              "n_sel=%d w=%d do not fit L=%d", n_sel, w, L);
+  KVC_REQUIRE(elem_bytes == 2 || elem_bytes == 4, KVC_ERR_UNSUPPORTED, "elem_bytes %d", elem_bytes);
+  return gather_dense(k, k_sb, k_sh, k_sl, v, v_sb, v_sh, v_sl, idx, B, Hq, Hkv, L, d, n_sel, w, elem_bytes, out_k,
+                      out_v, (cudaStream_t)stream);
+}
+
+int kvc_gather_varlen(const void* k, int64_t k_sh, int64_t k_sl, const void* v, int64_t v_sh, int64_t v_sl,
+                      const int32_t* idx, int64_t idx_stride, const int32_t* cap, const int32_t* cu_klen, int Hq,
+                      int Hkv, int L, int d, int w, int max_cap, int elem_bytes, void* out_k, void* out_v,
+                      void* stream) {
+  if (int rc = check_device()) return rc;
+  KVC_REQUIRE(k && v && idx && cap && cu_klen && out_k && out_v, KVC_ERR_ARG, "null pointer argument");
+  KVC_REQUIRE(Hq > 0 && Hkv > 0 && Hq % Hkv == 0 && L > 0 && d > 0 && w >= 0 && max_cap >= 0, KVC_ERR_ARG,
+              "bad head geometry");
+  KVC_REQUIRE(elem_bytes == 2 || elem_bytes == 4, KVC_ERR_UNSUPPORTED, "elem_bytes %d", elem_bytes);
+  return gather_varlen(k, k_sh, k_sl, v, v_sh, v_sl, idx, idx_stride, cap, cu_klen, Hq, Hkv, L, d, w, max_cap,
+                       elem_bytes, out_k, out_v, (cudaStream_t)stream);
+}
+
+size_t kvc_adakv_allocate_workspace_bytes(int H, int n) {
+  if (H <= 0 || n <= 0) return 0;
+  return adakv_allocate_workspace_bytes(H, n);
+}
+
+int kvc_adakv_allocate(const void* pooled, const float* sums, int H, int n, int dtype, int base_capacity,
+                       float one_minus_floor, int floor_capacity, int normalize, int w, int32_t* out_cap,
+                       int32_t* out_head_lens, int32_t* out_cu_klen, void* workspace, size_t workspace_bytes,
+                       void* stream) {
+  if (int rc = check_device()) return rc;
+  KVC_REQUIRE(pooled && sums && out_cap && out_head_lens && out_cu_klen && workspace, KVC_ERR_ARG, "null pointer");
+  KVC_REQUIRE(H > 0 && n > 0 && base_capacity > 0 && base_capacity <= n, KVC_ERR_ARG,
+              "H=%d n=%d base_capacity=%d", H, n, base_capacity);
+  KVC_REQUIRE(dtype == KVC_BF16 || dtype == KVC_FP16, KVC_ERR_UNSUPPORTED, "dtype %d", dtype);
+  return adakv_allocate(pooled, sums, H, n, dtype, base_capacity, one_minus_floor, floor_capacity, normalize, w,
+                        out_cap, out_head_lens, out_cu_klen, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int kvc_update_flatten_view(void* dst, const void* src, const void* state, const int32_t* headlens,
+                            const int32_t* cu_headlens, int H, int d, int elem_bytes, int64_t total_rows,
+                            void* stream) {
+  if (int rc = check_device()) return rc;
+  KVC_REQUIRE(dst && src && state && headlens && cu_headlens, KVC_ERR_ARG, "null pointer argument");
+  KVC_REQUIRE(H > 0 && d > 0 && total_rows >= 0, KVC_ERR_ARG, "H=%d d=%d total_rows=%lld", H, d, (long long)total_rows);
+  KVC_REQUIRE(elem_bytes == 2, KVC_ERR_UNSUPPORTED,
+              "elem_bytes %d: the reference kernel is fp16/bf16 only (static_switch.h:3-12)", elem_bytes);
+  return update_flatten_view(dst, src, state, headlens, cu_headlens, H, d, elem_bytes, total_rows,
+                             (cudaStream_t)stream);
+}
+
+}  // extern "C"

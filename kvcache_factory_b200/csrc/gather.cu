@@ -1,0 +1,162 @@
+// Row movers: dense/varlen gather-compact of the selected K,V rows and the flattened-cache append.
+// Pure HBM traffic: every row is moved as 16-byte vectors (a d=128 bf16 row is 256 B = 16 lanes),
+// several rows in flight per thread, streaming (no-L1-allocate) loads and stores.
+#include "common.cuh"
+
+namespace kvc {
+
+constexpr int kGatherThreads = 256;
+constexpr int kGatherUnroll = 4;
+
+struct RowSrc {
+  const char* base;  // tensor base
+  int64_t sb, sh, sl;  // byte strides
+};
+
+// One thread moves one 16-B chunk of kGatherUnroll rows of K and of V.
+// rows are numbered over [units, rows_per_unit]; unit = b*Hq + h.
+template <bool kVarlen>
+__global__ void __launch_bounds__(kGatherThreads)
+gather_rows_kernel(RowSrc ksrc, RowSrc vsrc, const int32_t* __restrict__ idx, int64_t idx_stride,
+                   const int32_t* __restrict__ cap, const int32_t* __restrict__ cu_klen,
+                   int Hq, int groups, int L, int w, int n_sel, int chunks_per_row,
+                   char* __restrict__ out_k, char* __restrict__ out_v) {
+  const int unit = blockIdx.y;
+  const int b = unit / Hq, h = unit % Hq;
+  const int nsel = kVarlen ? cap[h] : n_sel;
+  const int rows = nsel + w;
+  const int64_t out_row0 = kVarlen ? (int64_t)cu_klen[h] : (int64_t)unit * rows;
+  const int rows_per_pass = kGatherThreads / chunks_per_row;
+  const int c = threadIdx.x % chunks_per_row;
+  const int rg = threadIdx.x / chunks_per_row;
+  if (rg >= rows_per_pass) return;
+  const int block_rows = rows_per_pass * kGatherUnroll;
+  const int r0 = blockIdx.x * block_rows + rg;
+  if (blockIdx.x * block_rows >= rows) return;
+
+  const int64_t rowbytes = (int64_t)chunks_per_row * 16;
+  const char* kbase = ksrc.base + b * ksrc.sb + (h / groups) * ksrc.sh + c * 16;
+  const char* vbase = vsrc.base + b * vsrc.sb + (h / groups) * vsrc.sh + c * 16;
+  const int32_t* my_idx = idx ? idx + (int64_t)unit * idx_stride : nullptr;
+
+  int srow[kGatherUnroll];
+#pragma unroll
+  for (int u = 0; u < kGatherUnroll; ++u) {
+    const int r = r0 + u * rows_per_pass;
+    int s = -1;
+    if (r < rows) s = (r < nsel) ? (my_idx ? my_idx[r] : r) : (L - w + (r - nsel));
+    srow[u] = s;
+  }
+  int4 kv[kGatherUnroll], vv[kGatherUnroll];
+#pragma unroll
+  for (int u = 0; u < kGatherUnroll; ++u) {
+    if (srow[u] >= 0) {
+      kv[u] = ld_stream16(kbase + (int64_t)srow[u] * ksrc.sl);
+      vv[u] = ld_stream16(vbase + (int64_t)srow[u] * vsrc.sl);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < kGatherUnroll; ++u) {
+    if (srow[u] >= 0) {
+      const int64_t off = (out_row0 + r0 + u * rows_per_pass) * rowbytes + c * 16;
+      st_stream16(out_k + off, kv[u]);
+      st_stream16(out_v + off, vv[u]);
+    }
+  }
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+static int check_rows(const void* k, const void* v, int64_t rowbytes, int64_t ksb, int64_t ksh, int64_t ksl,
+                      int64_t vsb, int64_t vsh, int64_t vsl, int e, const void* ok, const void* ov) {
+  KVC_REQUIRE(rowbytes % 16 == 0 && rowbytes <= 16 * kGatherThreads, KVC_ERR_UNSUPPORTED,
+              "row of %lld bytes: need a multiple of 16 B and <= %d B", (long long)rowbytes, 16 * kGatherThreads);
+  KVC_REQUIRE(aligned16(k) && aligned16(v) && aligned16(ok) && aligned16(ov), KVC_ERR_UNSUPPORTED,
+              "K/V/out pointers must be 16-byte aligned");
+  KVC_REQUIRE((ksb * e) % 16 == 0 && (ksh * e) % 16 == 0 && (ksl * e) % 16 == 0 && (vsb * e) % 16 == 0 &&
+                  (vsh * e) % 16 == 0 && (vsl * e) % 16 == 0,
+              KVC_ERR_UNSUPPORTED, "K/V strides must be multiples of 16 bytes");
+  return 0;
+}
+
+int gather_dense(const void* k, int64_t k_sb, int64_t k_sh, int64_t k_sl, const void* v, int64_t v_sb,
+                 int64_t v_sh, int64_t v_sl, const int32_t* idx, int B, int Hq, int Hkv, int L, int d, int n_sel,
+                 int w, int e, void* out_k, void* out_v, cudaStream_t stream) {
+  const int64_t rowbytes = (int64_t)d * e;
+  if (int rc = check_rows(k, v, rowbytes, k_sb, k_sh, k_sl, v_sb, v_sh, v_sl, e, out_k, out_v)) return rc;
+  const int cpr = (int)(rowbytes / 16);
+  const int rows = n_sel + w;
+  const int block_rows = (kGatherThreads / cpr) * kGatherUnroll;
+  dim3 grid((rows + block_rows - 1) / block_rows, B * Hq);
+  RowSrc ks{(const char*)k, k_sb * e, k_sh * e, k_sl * e}, vs{(const char*)v, v_sb * e, v_sh * e, v_sl * e};
+  gather_rows_kernel<false><<<grid, kGatherThreads, 0, stream>>>(ks, vs, idx, n_sel, nullptr, nullptr, Hq, Hq / Hkv,
+                                                                  L, w, n_sel, cpr, (char*)out_k, (char*)out_v);
+  return launch_status("gather_rows_kernel<dense>");
+}
+
+int gather_varlen(const void* k, int64_t k_sh, int64_t k_sl, const void* v, int64_t v_sh, int64_t v_sl,
+                  const int32_t* idx, int64_t idx_stride, const int32_t* cap, const int32_t* cu_klen, int Hq,
+                  int Hkv, int L, int d, int w, int max_cap, int e, void* out_k, void* out_v,
+                  cudaStream_t stream) {
+  const int64_t rowbytes = (int64_t)d * e;
+  if (int rc = check_rows(k, v, rowbytes, 0, k_sh, k_sl, 0, v_sh, v_sl, e, out_k, out_v)) return rc;
+  const int cpr = (int)(rowbytes / 16);
+  const int rows = max_cap + w;
+  const int block_rows = (kGatherThreads / cpr) * kGatherUnroll;
+  dim3 grid((rows + block_rows - 1) / block_rows, Hq);
+  RowSrc ks{(const char*)k, 0, k_sh * e, k_sl * e}, vs{(const char*)v, 0, v_sh * e, v_sl * e};
+  gather_rows_kernel<true><<<grid, kGatherThreads, 0, stream>>>(ks, vs, idx, idx_stride, cap, cu_klen, Hq, Hq / Hkv,
+                                                                 L, w, 0, cpr, (char*)out_k, (char*)out_v);
+  return launch_status("gather_rows_kernel<varlen>");
+}
+
+// ---- flattened-cache append (cuda_api.cu:11-53 restated as a 16-byte segmented shift copy) ------
+// Head h's old rows move down by h rows; its new row lands right after them.  grid = (x, H); the
+// x-blocks of a head stride over that head's 16-byte chunks, kFlatUnroll chunks in flight.
+constexpr int kFlatThreads = 256;
+constexpr int kFlatUnroll = 4;
+
+__global__ void __launch_bounds__(kFlatThreads)
+flatten_append_kernel(char* __restrict__ dst, const char* __restrict__ src, const char* __restrict__ state,
+                      const int32_t* __restrict__ headlens, const int32_t* __restrict__ cu, int rowbytes) {
+  const int h = blockIdx.y;
+  const int64_t begin = cu[h];
+  const int64_t nchunks = (int64_t)headlens[h] * rowbytes / 16;
+  const char* s = src + begin * rowbytes;
+  char* d = dst + (begin + h) * rowbytes;
+  const int64_t stride = (int64_t)gridDim.x * kFlatThreads;
+  int64_t i = (int64_t)blockIdx.x * kFlatThreads + threadIdx.x;
+  for (; i + (kFlatUnroll - 1) * stride < nchunks; i += kFlatUnroll * stride) {
+    int4 t[kFlatUnroll];
+#pragma unroll
+    for (int u = 0; u < kFlatUnroll; ++u) t[u] = ld_stream16(s + (i + u * stride) * 16);
+#pragma unroll
+    for (int u = 0; u < kFlatUnroll; ++u) st_stream16(d + (i + u * stride) * 16, t[u]);
+  }
+  for (; i < nchunks; i += stride) st_stream16(d + i * 16, ld_stream16(s + i * 16));
+  if (blockIdx.x == 0 && threadIdx.x < rowbytes / 16) {
+    const int64_t ins = ((int64_t)cu[h + 1] + h) * rowbytes;
+    st_stream16(dst + ins + threadIdx.x * 16, ld_stream16(state + (int64_t)h * rowbytes + threadIdx.x * 16));
+  }
+}
+
+int update_flatten_view(void* dst, const void* src, const void* state, const int32_t* headlens,
+                        const int32_t* cu_headlens, int H, int d, int e, int64_t total_rows, cudaStream_t stream) {
+  const int rowbytes = d * e;
+  KVC_REQUIRE(rowbytes % 16 == 0, KVC_ERR_UNSUPPORTED, "row of %d bytes is not a multiple of 16", rowbytes);
+  KVC_REQUIRE(rowbytes <= 256, KVC_ERR_UNSUPPORTED,
+              "head_dim*elem_bytes = %d > 256 (the reference requires head_dim <= 128, cuda_api.cu:74)", rowbytes);
+  KVC_REQUIRE(aligned16(dst) && aligned16(src) && aligned16(state), KVC_ERR_UNSUPPORTED,
+              "cache/state pointers must be 16-byte aligned");
+  const int64_t chunks_per_head = (total_rows * rowbytes / 16 + H - 1) / H;
+  int64_t gx = (chunks_per_head + (int64_t)kFlatThreads * kFlatUnroll - 1) / ((int64_t)kFlatThreads * kFlatUnroll);
+  const int64_t cap_x = (int64_t)(8 * sm_count() + H - 1) / H;  // ~8 CTAs per SM over all heads
+  if (gx > cap_x) gx = cap_x;
+  if (gx < 1) gx = 1;
+  dim3 grid((unsigned)gx, H);
+  flatten_append_kernel<<<grid, kFlatThreads, 0, stream>>>((char*)dst, (const char*)src, (const char*)state, headlens,
+                                                           cu_headlens, rowbytes);
+  return launch_status("flatten_append_kernel");
+}
+
+}  // namespace kvc

@@ -1,0 +1,411 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle, the golden vectors made
+by the unmodified reference, and size-independent properties at BASELINE sizes.
+
+Tolerances (written here because they are the contract):
+  * gathers, appends, pooling, metadata: bit-exact.
+  * window scores: the kernel reproduces the reference's rounding points, so the only differences
+    are fp32 accumulation order inside the dot products and exp/ulp-level effects.  We require
+    every score within SCORE_ULPS model-dtype ulps of the oracle's and at least SCORE_EXACT_FRAC of
+    them bit-identical.
+  * index sets: identical except at near-ties: every position whose oracle score beats the k-th
+    value by more than TIE_RTOL (relative) must be selected and nothing below kth*(1-TIE_RTOL) may be.
+"""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from kvcache_factory_b200 import (AdaKVCluster, DynamicCacheSplitHeadFlatten, H2OKVCluster, PyramidKVCluster,
+                                  SnapKVCluster, StreamingLLMKVCluster, _native)
+from kvcache_factory_b200.synth import Shape, make_qkv
+from oracle import kvc_oracle as O
+from tests.helpers import DTYPES, from_bits, golden_cases, load_golden, score_mismatch, to_bits, ulp_of
+
+pytestmark = pytest.mark.gpu
+
+SCORE_ULPS = 4.0
+SCORE_EXACT_FRAC = 0.90
+TIE_RTOL = {torch.bfloat16: 2.0 ** -5, torch.float16: 2.0 ** -8}
+
+IMPLS = [pytest.param(_native.IMPL_MMA_SYNC, id="mma_sync"), pytest.param(_native.IMPL_TCGEN05, id="tcgen05")]
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def _skip_if_unsupported(fn):
+    try:
+        return fn()
+    except _native.KvcError as e:
+        if e.status == -2 and "tcgen05" in str(e):
+            pytest.skip(str(e))
+        raise
+
+
+# ------------------------------------------------------------------------------------------------
+# row movers
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("layout", ["unrepeated", "repeated", "hf_transposed"])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_gather_dense_bit_exact(layout, dtype):
+    shape = Shape(B=2, Hq=8, Hkv=2, L=777, d=128)
+    w, n_sel = 16, 200
+    g = torch.Generator().manual_seed(7)
+    _, K, V = make_qkv(shape, dtype, layer_idx=3, window=w)
+    idx = torch.stack([torch.randperm(shape.L - w, generator=g)[:n_sel] for _ in range(shape.B * shape.Hq)])
+    idx = idx.view(shape.B, shape.Hq, n_sel)
+    Kr, Vr = O.repeat_kv(K, 4), O.repeat_kv(V, 4)
+    ref_k, ref_v = O.gather_and_append_window(Kr, Vr, idx, w)
+    if layout == "unrepeated":
+        Kd, Vd = K.to(dev()), V.to(dev())
+    elif layout == "repeated":
+        Kd, Vd = Kr.to(dev()), Vr.to(dev())
+    else:  # memory order [B,L,H,d] viewed as [B,H,L,d], the layout RoPE output has in HF
+        Kd = K.to(dev()).transpose(1, 2).contiguous().transpose(1, 2)
+        Vd = V.to(dev()).transpose(1, 2).contiguous().transpose(1, 2)
+        assert not Kd.is_contiguous()
+    out_k, out_v = _native.gather_dense(Kd, Vd, idx.to(dev(), torch.int32).contiguous(), shape.Hq, n_sel, w)
+    assert torch.equal(out_k.cpu(), ref_k) and torch.equal(out_v.cpu(), ref_v)
+
+
+@pytest.mark.parametrize("name", golden_cases("streamingllm") + ["snapkv_passthrough"])
+def test_streamingllm_and_passthrough_match_reference_vectors(name):
+    c, z, (Q, K, V) = load_golden(name)
+    kn = c["knobs"]
+    Qd, Kd, Vd = Q.to(dev()), K.to(dev()), V.to(dev())
+    if c["method"] == "streamingllm":
+        cl = StreamingLLMKVCluster(**kn)
+        Kc, Vc = cl.update_kv(Kd, Qd, Vd, None, c["Hq"] // c["Hkv"])
+        assert np.array_equal(to_bits(Kc), z["K_out"]) and np.array_equal(to_bits(Vc), z["V_out"])
+    else:
+        cl = SnapKVCluster(**kn)
+        Kc, Vc = cl.update_kv(Kd, Qd, Vd, None, c["Hq"] // c["Hkv"])
+        assert Kc is Kd and Vc is Vd  # same objects, as in the reference (:314-315)
+
+
+def _flatten_case(H, d, lens, dtype, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    hl = np.asarray(lens, dtype=np.int32)
+    cu = np.concatenate([[0], np.cumsum(hl)]).astype(np.int32)
+    total = int(cu[-1])
+    cache = torch.randn(total, d, generator=g).to(dtype)
+    state = torch.randn(H, d, generator=g).to(dtype)
+    return cache, state, hl, cu
+
+
+@pytest.mark.parametrize("lens", [[5, 1, 9, 3], [0, 4, 0, 2], [1], [2080, 2011, 1999, 2100, 33, 4096, 2048, 1]])
+@pytest.mark.parametrize("d", [64, 128])
+def test_update_flatten_view_matches_oracles(lens, d):
+    H = len(lens)
+    cache, state, hl, cu = _flatten_case(H, d, lens, torch.float16)
+    out = _native.update_flatten_view(cache.to(dev()), state.to(dev()), torch.from_numpy(hl).to(dev()),
+                                      torch.from_numpy(cu).to(dev()))
+    got = to_bits(out)
+    ref = O.update_flatten_view(to_bits(cache), to_bits(state), hl, cu)
+    assert got.shape == (cache.shape[0] + H, d) and np.array_equal(got, ref)
+    # the plain-C restatement of cuda_api.cu agrees too
+    so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_build",
+                      "libflatten_oracle.so")
+    if os.path.exists(so):
+        lib = ctypes.CDLL(so)
+        dst = np.zeros_like(ref)
+        src, st = np.ascontiguousarray(to_bits(cache)), np.ascontiguousarray(to_bits(state))
+        lib.flatten_oracle_update(dst.ctypes.data_as(ctypes.c_void_p), src.ctypes.data_as(ctypes.c_void_p),
+                                  st.ctypes.data_as(ctypes.c_void_p), hl.ctypes.data_as(ctypes.c_void_p),
+                                  cu.ctypes.data_as(ctypes.c_void_p), ctypes.c_int32(H), ctypes.c_int32(d))
+        assert np.array_equal(got, dst)
+
+
+def test_update_flatten_view_errors_like_reference():
+    cache, state, hl, cu = _flatten_case(2, 128, [3, 4], torch.bfloat16)
+    with pytest.raises(RuntimeError, match="int32"):
+        _native.update_flatten_view(cache.to(dev()), state.to(dev()), torch.from_numpy(hl).long().to(dev()),
+                                    torch.from_numpy(cu).to(dev()))
+    big = torch.zeros(4, 256, dtype=torch.bfloat16, device=dev())
+    with pytest.raises(RuntimeError):
+        _native.update_flatten_view(big, big[:2], torch.from_numpy(hl).to(dev()), torch.from_numpy(cu).to(dev()))
+
+
+def test_flatten_cache_decode_steps():
+    """DynamicCacheSplitHeadFlatten: prefill append then 3 decode appends with the metadata bumps of
+    llama_model.py:2372-2375; every head's rows must stay in order with the new rows at the end."""
+    H, d = 4, 128
+    lens = [7, 3, 5, 9]
+    cache, _, hl, cu = _flatten_case(H, d, lens, torch.bfloat16, seed=1)
+    kc = DynamicCacheSplitHeadFlatten()
+    kc.update(cache.to(dev()), cache.to(dev()).clone(), 0)
+    head_lens = torch.from_numpy(hl).to(dev())
+    cu_klen = torch.from_numpy(cu).to(dev())
+    cu_offset = torch.arange(0, H + 1, dtype=torch.int32, device=dev())
+    per_head = [cache[cu[h]:cu[h + 1]].clone() for h in range(H)]
+    for step in range(3):
+        new = torch.randn(1, H, 1, d).to(torch.bfloat16)
+        k, v = kc.update(new.to(dev()), new.to(dev()), 0, {"head_lens": head_lens, "cu_klen": cu_klen})
+        cu_klen = cu_klen + cu_offset
+        head_lens = head_lens + 1
+        per_head = [torch.cat([per_head[h], new[0, h]], 0) for h in range(H)]
+        assert torch.equal(k.cpu(), torch.cat(per_head, 0)) and torch.equal(v.cpu(), torch.cat(per_head, 0))
+
+
+# ------------------------------------------------------------------------------------------------
+# pool + top-k
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("pooling,kernel", [("avgpool", 7), ("avgpool", 5), ("maxpool", 7), ("maxpool", 1), (None, 1)])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("n,k", [(4064, 96), (1000, 1000), (333, 1), (20000, 3932), (70000, 9000)])
+def test_pool_topk_matches_torch(pooling, kernel, dtype, n, k):
+    g = torch.Generator().manual_seed(n + k)
+    rows = 6
+    s = (torch.rand(rows, n, generator=g) ** 4 * 3).to(dtype)           # many exact ties in 16-bit
+    ref_pooled = O.pool_scores(s.view(1, rows, n), kernel, pooling).view(rows, n)
+    idx, pooled, sums = _native.pool_topk(s.to(dev()), kernel, pooling, k, want_pooled=True, want_sums=True)
+    assert np.array_equal(to_bits(pooled), to_bits(ref_pooled)), "pooled scores are not bit-identical to ATen's"
+    idx = idx.cpu().long()
+    vals = ref_pooled.float().gather(1, idx)
+    ref_vals = ref_pooled.float().topk(k, dim=-1).values
+    assert torch.equal(vals, ref_vals), "selected values (descending) differ from torch.topk"
+    for r in range(rows):
+        assert idx[r].unique().numel() == k
+        same = vals[r][1:] == vals[r][:-1]
+        assert bool((idx[r][1:][same] > idx[r][:-1][same]).all()), "ties must be ordered by ascending position"
+    assert torch.allclose(sums[:, 0].cpu(), ref_vals.sum(-1), rtol=1e-5)
+    assert torch.allclose(sums[:, 1].cpu(), ref_pooled.float().sum(-1), rtol=1e-5)
+
+
+def test_pool_topk_per_row_k():
+    g = torch.Generator().manual_seed(5)
+    rows, n = 8, 5000
+    s = torch.rand(rows, n, generator=g).to(torch.bfloat16)
+    kk = torch.tensor([0, 1, 17, 4999, 5000, 2048, 100, 3], dtype=torch.int32)
+    idx, _, _ = _native.pool_topk(s.to(dev()), 7, "maxpool", 5000, k_per_row=kk.to(dev()))
+    ref_pooled = O.pool_scores(s.view(1, rows, n), 7, "maxpool").view(rows, n).float()
+    for r in range(rows):
+        k = int(kk[r])
+        if k:
+            assert torch.equal(ref_pooled[r][idx[r, :k].cpu().long()], ref_pooled[r].topk(k).values)
+
+
+def test_pool_topk_errors():
+    s = torch.zeros(2, 100, dtype=torch.bfloat16, device=dev())
+    with pytest.raises(ValueError, match="Pooling method not supported"):
+        _native.pool_topk(s, 5, "medianpool", 10)
+    with pytest.raises(_native.KvcError):
+        _native.pool_topk(s, 4, "avgpool", 10)        # even kernels change the length in the reference
+    with pytest.raises(_native.KvcError):
+        _native.pool_topk(s, 5, "avgpool", 101)       # k > n: torch.topk raises too
+
+
+# ------------------------------------------------------------------------------------------------
+# window scores
+# ------------------------------------------------------------------------------------------------
+SCORE_CASES = [
+    # B, Hq, Hkv, L, d, w
+    (1, 8, 2, 512, 128, 32),
+    (2, 4, 4, 300, 128, 8),       # repeated layout (g = 1), ragged L
+    (1, 4, 1, 641, 128, 32),
+    (1, 16, 2, 1500, 128, 32),    # g = 8 (70B geometry): 256 stacked rows
+    (1, 6, 3, 333, 64, 16),       # d = 64
+    (1, 4, 2, 200, 128, 20),      # window not a multiple of 16
+    (1, 32, 8, 4096, 128, 32),    # cfg-1 geometry
+]
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("reduce", ["sum", "mean"])
+@pytest.mark.parametrize("case", SCORE_CASES, ids=lambda c: "B%d_Hq%d_Hkv%d_L%d_d%d_w%d" % c)
+def test_window_scores_match_oracle(impl, dtype, reduce, case):
+    B, Hq, Hkv, L, d, w = case
+    shape = Shape(B, Hq, Hkv, L, d)
+    Q, K, V = make_qkv(shape, dtype, layer_idx=1, dist="peaked", window=w)
+    ref = O.window_scores(O.repeat_kv(K, Hq // Hkv), Q, w, reduce)
+    got = _skip_if_unsupported(lambda: _native.window_scores(Q.to(dev()), K.to(dev()), w, reduce, impl))
+    torch.cuda.synchronize()
+    assert got.shape == ref.shape and got.dtype == dtype
+    bad, worst = score_mismatch(got, ref, dtype, SCORE_ULPS)
+    exact = float((got.cpu() == ref).float().mean())
+    assert bad == 0.0, f"{bad:.2%} of scores off by more than {SCORE_ULPS} ulps (worst {worst:.1f}x)"
+    assert exact >= SCORE_EXACT_FRAC, f"only {exact:.2%} of scores bit-identical to the oracle"
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_window_scores_hf_query_layout(impl):
+    """query_states arrives as a transposed view of [B,L,Hq,d]: same result."""
+    shape = Shape(1, 8, 2, 700, 128)
+    Q, K, _ = make_qkv(shape, torch.bfloat16, layer_idx=2, dist="peaked", window=32)
+    a = _skip_if_unsupported(lambda: _native.window_scores(Q.to(dev()), K.to(dev()), 32, "sum", impl))
+    Qt = Q.to(dev()).transpose(1, 2).contiguous().transpose(1, 2)
+    Kt = K.to(dev()).transpose(1, 2).contiguous().transpose(1, 2)
+    b = _native.window_scores(Qt, Kt, 32, "sum", impl)
+    assert torch.equal(a, b)
+
+
+# ------------------------------------------------------------------------------------------------
+# whole update_kv against the reference's vectors
+# ------------------------------------------------------------------------------------------------
+def _check_dense(cluster, c, z, Q, K, V, impl):
+    dtype = DTYPES[c["dtype"]]
+    g = c["Hq"] // c["Hkv"]
+    cluster.keep_debug = True
+    cluster.score_impl = impl
+    Kc, Vc = _skip_if_unsupported(lambda: cluster.update_kv(K.to(dev()), Q.to(dev()), V.to(dev()), None, g))
+    torch.cuda.synchronize()
+    assert tuple(Kc.shape) == tuple(z["K_out"].shape) and Kc.dtype == dtype
+    idx = cluster.debug["indices"].cpu().long()
+    pooled_ref = from_bits(z["pooled"], dtype)
+    k = z["idx"].shape[-1]
+    ok, msg = O.check_index_sets(pooled_ref, idx, k, rtol=TIE_RTOL[dtype])
+    assert ok, msg
+    # given the indices, the gathered rows are bit-exact
+    w = c["knobs"]["window_size"]
+    Kr, Vr = O.repeat_kv(K, g), O.repeat_kv(V, g)
+    gk, gv = O.gather_and_append_window(Kr, Vr, idx, w)
+    assert torch.equal(Kc.cpu(), gk) and torch.equal(Vc.cpu(), gv)
+    # how close the selection is to the reference's own (reported, ties make 100% unattainable)
+    ref_sets = z["idx"]
+    agree = np.mean([len(set(idx[b, h].tolist()) & set(ref_sets[b, h].tolist())) / k
+                     for b in range(idx.shape[0]) for h in range(idx.shape[1])])
+    assert agree > 0.9, f"only {agree:.1%} of the reference's picks were selected"
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("name", golden_cases("snapkv"))
+def test_snapkv_matches_reference_vectors(name, impl):
+    if name == "snapkv_passthrough":
+        pytest.skip("covered by the pass-through test")
+    c, z, (Q, K, V) = load_golden(name)
+    _check_dense(SnapKVCluster(**c["knobs"]), c, z, Q, K, V, impl)
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("name", golden_cases("pyramidkv"))
+def test_pyramidkv_matches_reference_vectors(name, impl):
+    c, z, (Q, K, V) = load_golden(name)
+    _check_dense(PyramidKVCluster(**c["knobs"]), c, z, Q, K, V, impl)
+
+
+def test_repeated_layout_gives_same_result_as_unrepeated():
+    shape = Shape(1, 8, 2, 600, 128)
+    Q, K, V = make_qkv(shape, torch.bfloat16, layer_idx=4, dist="peaked", window=32)
+    a = SnapKVCluster(32, 128, 7, "avgpool")
+    b = SnapKVCluster(32, 128, 7, "avgpool")
+    a.score_impl = b.score_impl = _native.IMPL_MMA_SYNC
+    Ka, Va = a.update_kv(K.to(dev()), Q.to(dev()), V.to(dev()), None, 4)
+    Kb, Vb = b.update_kv(O.repeat_kv(K, 4).to(dev()), Q.to(dev()), O.repeat_kv(V, 4).to(dev()), None, 4)
+    assert torch.equal(Ka, Kb) and torch.equal(Va, Vb)
+
+
+def test_cluster_errors_like_reference():
+    with pytest.raises(AssertionError):
+        SnapKVCluster(window_size=64, max_capacity_prompt=64)
+    shape = Shape(1, 4, 2, 256, 128)
+    Q, K, V = make_qkv(shape, torch.bfloat16, window=16)
+    cl = SnapKVCluster(16, 64, 5, "medianpool")
+    with pytest.raises(ValueError, match="Pooling method not supported"):
+        cl.update_kv(K.to(dev()), Q.to(dev()), V.to(dev()), None, 2)
+    with pytest.raises(AssertionError):
+        SnapKVCluster(16, 64, 5, "avgpool").update_kv(K.to(dev())[:, :, :100], Q.to(dev()), V.to(dev()), None, 2)
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        SnapKVCluster(16, 64, 5, "avgpool").update_kv(K, Q, V, None, 2)
+    with pytest.raises(TypeError):
+        SnapKVCluster(16, 64, 5, "avgpool").update_kv(K.float().to(dev()), Q.float().to(dev()), V.float().to(dev()),
+                                                      None, 2)
+
+
+# ------------------------------------------------------------------------------------------------
+# AdaKV
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", golden_cases("adakv"))
+def test_adakv_matches_reference_vectors(name):
+    c, z, (Q, K, V) = load_golden(name)
+    kn = c["knobs"]
+    dtype = DTYPES[c["dtype"]]
+    w, H, d = kn["window_size"], c["Hq"], c["d"]
+    cl = AdaKVCluster(**kn)
+    cl.keep_debug = True
+    cl.score_impl = _native.IMPL_MMA_SYNC
+    fk, fv = cl.update_kv(K.to(dev()), Q.to(dev()), V.to(dev()))
+    torch.cuda.synchronize()
+    # metadata contract (dtypes, shapes, internal consistency)
+    for a in ("head_lens", "cu_klen", "cu_headlens", "cu_qlen", "cu_offset", "cu_head_offset", "layer_qlens"):
+        t = getattr(cl, a)
+        assert t.dtype == torch.int32 and tuple(t.shape) == tuple(z["meta_" + a].shape), a
+    for a in ("cu_qlen", "cu_offset", "cu_head_offset", "layer_qlens"):
+        assert np.array_equal(getattr(cl, a).cpu().numpy(), z["meta_" + a]), a
+    hl = cl.head_lens.cpu().numpy()
+    cu = cl.cu_klen.cpu().numpy()
+    assert np.array_equal(cu, np.concatenate([[0], np.cumsum(hl)])) and cl.klen_sum == int(hl.sum()) == fk.shape[0]
+    assert np.array_equal(cl.cu_headlens.cpu().numpy(), np.cumsum(hl)) and cl.max_seqlen_k == int(hl.max())
+    assert cl.qlen_sum == H
+    if name == "adakv_nocompress":
+        assert np.array_equal(hl, z["meta_head_lens"])
+        assert np.array_equal(to_bits(fk), z["K_out"]) and np.array_equal(to_bits(fv), z["V_out"])
+        return
+    # capacities: torch's global topk breaks ties arbitrarily, so a head may differ from the reference by
+    # at most the number of its scores tied at the global threshold; the total is tie-independent up to rounding
+    ref_hl = z["meta_head_lens"]
+    pooled_ref = from_bits(z["pooled"], dtype)
+    cap_ref, _, adaptive = O.adakv_capacities(pooled_ref, kn["max_capacity_prompt"] - w, kn["floor"], kn["normalize"])
+    flat = adaptive.float().reshape(-1)
+    kth = flat.topk(H * (kn["max_capacity_prompt"] - w)).values[-1]
+    ties = (adaptive.float()[0] == kth).sum(-1).numpy()
+    assert np.all(np.abs(hl - ref_hl) <= ties * (1 - kn["floor"]) + 1), (hl, ref_hl, ties)
+    assert abs(int(hl.sum()) - int(ref_hl.sum())) <= H
+    # per head: the kept rows are that head's top-cap rows (tie-aware) followed by the window, bit-exact
+    g = c["Hq"] // c["Hkv"]
+    Kr, Vr = O.repeat_kv(K, g), O.repeat_kv(V, g)
+    idx = cl.debug["indices"].cpu().long()
+    for h in range(H):
+        cap = int(hl[h]) - w
+        sel = idx[h, :cap]
+        ok, msg = O.check_index_sets(pooled_ref[:, h:h + 1], sel.view(1, 1, -1), cap, rtol=TIE_RTOL[dtype])
+        assert ok, f"head {h}: {msg}"
+        rows_k = torch.cat([Kr[0, h, :-w][sel], Kr[0, h, -w:]], 0)
+        rows_v = torch.cat([Vr[0, h, :-w][sel], Vr[0, h, -w:]], 0)
+        assert torch.equal(fk[cu[h]:cu[h + 1]].cpu(), rows_k) and torch.equal(fv[cu[h]:cu[h + 1]].cpu(), rows_v)
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE sizes: size-independent properties
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("impl", IMPLS)
+def test_pyramidkv_full_size_properties(impl):
+    """cfg-2 geometry (Llama-3-8B heads, L=32768, cap 2048, w=32, avgpool 7), two layers."""
+    shape = Shape(1, 32, 8, 32768, 128)
+    w, cap = 32, 2048
+    for layer in (0, 31):
+        Q, K, V = make_qkv(shape, torch.bfloat16, layer_idx=layer, dist="peaked", window=w, q_window_only=True)
+        Qd, Kd, Vd = Q.to(dev()), K.to(dev()), V.to(dev())
+        cl = PyramidKVCluster(num_hidden_layers=32, window_size=w, max_capacity_prompt=cap, kernel_size=7,
+                              pooling="avgpool", layer_idx=layer)
+        cl.keep_debug = True
+        cl.score_impl = impl
+        Kc, Vc = _skip_if_unsupported(lambda: cl.update_kv(Kd, Qd, Vd, None, 4))
+        torch.cuda.synchronize()
+        budget = O.pyramidkv_budget(shape.L, w, cap, 32, layer)
+        assert Kc.shape == (1, 32, budget + w, 128)
+        idx = cl.debug["indices"].long()
+        scores = cl.debug["scores"].float()
+        # probabilities of each window row sum to <= 1 over the non-window keys
+        assert float(scores.sum(-1).max()) <= w * (1 + 2.0 ** -6)
+        assert float(scores.min()) >= 0.0
+        # indices: distinct, in range, ordered by descending pooled score
+        assert int(idx.min()) >= 0 and int(idx.max()) < shape.L - w
+        srt = idx.sort(-1).values
+        assert bool((srt[..., 1:] != srt[..., :-1]).all())
+        pooled = cl.debug["pooled"].float()
+        pv = pooled.gather(-1, idx)
+        assert bool((pv[..., 1:] <= pv[..., :-1]).all())
+        kth = pv[..., -1:]
+        assert bool(((pooled > kth).sum(-1) <= budget).all()), "something above the threshold was left out"
+        # gather round trip: output rows are exactly the addressed input rows (checked with torch on the GPU)
+        Kr = Kd.repeat_interleave(4, dim=1)
+        assert torch.equal(Kc[:, :, :budget], Kr.gather(2, idx.unsqueeze(-1).expand(-1, -1, -1, 128)))
+        assert torch.equal(Kc[:, :, budget:], Kr[:, :, -w:])
+        Vr = Vd.repeat_interleave(4, dim=1)
+        assert torch.equal(Vc[:, :, :budget], Vr.gather(2, idx.unsqueeze(-1).expand(-1, -1, -1, 128)))
+        # the planted heavy hitters (1 % of positions, +4*qbar) dominate the selection
+        del Kr, Vr
