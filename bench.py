@@ -1,0 +1,401 @@
+#!/usr/bin/env python
+"""bench.py — KV tokens compressed / second on BASELINE.json's headline configuration.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+Workload (default ``pyramidkv_llama3_8b_32k`` = BASELINE.json configs[1]): PyramidKV compression of a
+32-layer Llama-3-8B prefill (32 query / 8 KV heads, d=128, bf16) of 32 768 tokens to budget 2048
+(window 32, avg-pool 7).  One "step" = ``update_kv`` of all 32 layers on synthetic N(0,1) K/V/Q.
+Metric = B*L / time-per-step, whole job over all ranks.
+
+Legs printed in ONE JSON line (rank 0):
+  value        device-resident inputs, CUDA events around exactly K steps, max over ranks
+  e2e          same metric through the host-buffer API: pinned host K/V/Q-window -> device,
+               compress, compressed K'/V' -> host, all inside the timed region
+  roofline     dominant kernel (time share measured with CUDA events inside the timed region):
+               algorithmic bytes per launch / its mean duration vs MEASURED_PEAKS.json
+  cpu_baseline the oracle (torch CPU restatement of the reference) on a bounded sample, rank 0, N=1
+``--impl reference`` times that CPU restatement alone on the same workload (bounded sample per step).
+
+Multi-GPU (torchrun, one rank per GPU): the (batch, KV-head) units of an N-request batch are sharded
+over the ranks, 8 units per rank as at N=1, with no data-path collective ("scaling": "weak").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[1]
+    "pyramidkv_llama3_8b_32k": dict(method="pyramidkv", B=1, Hq=32, Hkv=8, d=128, L=32768, layers=32, window=32,
+                                    cap=2048, kernel=7, pooling="avgpool", dtype="bf16"),
+    # configs[0]: the reference's own CPU-runnable case (one layer)
+    "snapkv_llama3_8b_4k_1layer": dict(method="snapkv", B=1, Hq=32, Hkv=8, d=128, L=4096, layers=1, window=32,
+                                       cap=128, kernel=7, pooling="avgpool", dtype="bf16"),
+    # configs[4] per-GPU shard at 8 GPUs is 1 KV head; at N=1 this is the whole 70B layer stack
+    "pyramidkv_llama3_70b_128k": dict(method="pyramidkv", B=1, Hq=64, Hkv=8, d=128, L=131072, layers=80, window=32,
+                                      cap=2048, kernel=7, pooling="avgpool", dtype="bf16"),
+}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi in the background during the timed region)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.samples, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# algorithmic bytes
+# ------------------------------------------------------------------------------------------------
+def kept_rows(wl, layer):
+    from kvcache_factory_b200 import pyramid_budget
+    if wl["method"] == "pyramidkv":
+        base = wl["cap"] - wl["window"]
+        if wl["L"] < wl["cap"]:
+            return wl["L"]
+        if wl["L"] < 2 * base:
+            return wl["cap"]
+        return pyramid_budget(wl["L"], wl["window"], wl["cap"], wl["layers"], layer) + wl["window"]
+    return wl["cap"]
+
+
+def alg_bytes_layer(wl, layer, B=None, Hq=None, Hkv=None):
+    e = 2
+    B = B or wl["B"]; Hq = Hq or wl["Hq"]; Hkv = Hkv or wl["Hkv"]
+    score = B * Hkv * wl["L"] * wl["d"] * e + B * Hq * wl["window"] * wl["d"] * e
+    C = kept_rows(wl, layer)
+    gather = 4 * B * Hq * C * wl["d"] * e
+    if wl["method"] == "streamingllm":
+        score = 0
+    return score, gather
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle on host cores, bounded sample
+# ------------------------------------------------------------------------------------------------
+def cpu_reference(wl, sample_layers, repeats=1):
+    """Time the CPU restatement of the reference's update_kv (oracle/kvc_oracle.py, the same ATen op
+    chain incl. repeat_kv as every reference call site) on `sample_layers`; returns
+    (tokens/s extrapolated to all layers, seconds per layer, cores)."""
+    import torch
+    from kvcache_factory_b200.synth import Shape, make_qkv
+    from oracle import kvc_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    shape = Shape(wl["B"], wl["Hq"], wl["Hkv"], wl["L"], wl["d"])
+    dtype = torch.bfloat16 if wl["dtype"] == "bf16" else torch.float16
+    times = []
+    for layer in sample_layers:
+        Q, K, V = make_qkv(shape, dtype, layer_idx=layer, window=wl["window"], q_window_only=True)
+        best = None
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            if wl["method"] == "pyramidkv":
+                O.pyramidkv_update_kv(K, Q, V, layer, wl["layers"], wl["window"], wl["cap"], wl["kernel"], wl["pooling"])
+            else:
+                O.snapkv_update_kv(K, Q, V, wl["window"], wl["cap"], wl["kernel"], wl["pooling"])
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        times.append(best)
+    per_layer = sum(times) / len(times)
+    return wl["B"] * wl["L"] / (per_layer * wl["layers"]), per_layer, cores
+
+
+def run_reference(args, wl):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    n = wl["layers"]
+    sample = sorted(set([0, n // 2, n - 1]))[: max(1, min(3, n))]
+    for _ in range(min(args.warmup, 1)):
+        cpu_reference(wl, sample[:1])
+    vals = []
+    t_all = time.perf_counter()
+    for _ in range(max(1, args.steps)):
+        v, per_layer, cores = cpu_reference(wl, sample)
+        vals.append(v)
+    ms_step = (time.perf_counter() - t_all) * 1e3 / max(1, args.steps)
+    value = statistics.median(vals)
+    desc = (f"oracle/kvc_oracle.py (torch CPU restatement of update_kv incl. repeat_kv), layers {sample} of "
+            f"{n} at full L={wl['L']}, mean per-layer time x {n} layers")
+    line = {
+        "impl": "reference", "metric": "kv_tokens_compressed_per_s", "value": value, "unit": "tokens/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": wl["dtype"], "data": "synthetic",
+        "config": config_of(args.workload, wl, 1),
+        "cpu_baseline": {"value": value, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def config_of(name, wl, world):
+    return {"workload": name, "method": wl["method"], "heads": f"{wl['Hq']}q/{wl['Hkv']}kv", "head_dim": wl["d"],
+            "seq_len": wl["L"], "layers": wl["layers"], "window_size": wl["window"],
+            "max_capacity_prompt": wl["cap"], "kernel_size": wl["kernel"], "pooling": wl["pooling"],
+            "batch_per_gpu": wl["B"], "sharding": f"{wl['B'] * wl['Hkv']} (batch,kv-head) units per GPU x {world}",
+            "l2": "inputs larger than L2 (4 GiB of K/V per step per GPU)"}
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, wl):
+    import torch
+    rank, world, local = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    from kvcache_factory_b200 import PyramidKVCluster, SnapKVCluster, _native
+    from kvcache_factory_b200.host_api import HostCompressor
+
+    B, Hq, Hkv, L, d, w, nl = wl["B"], wl["Hq"], wl["Hkv"], wl["L"], wl["d"], wl["window"], wl["layers"]
+    dtype = torch.bfloat16 if wl["dtype"] == "bf16" else torch.float16
+    impl = {"auto": _native.IMPL_AUTO, "mma": _native.IMPL_MMA_SYNC, "tc": _native.IMPL_TCGEN05}[args.score_impl]
+
+    # synthetic inputs, device resident; each rank draws its own shard of the N-request batch
+    g = torch.Generator(device=dev)
+    Ks, Vs, Qs, clusters = [], [], [], []
+    for layer in range(nl):
+        g.manual_seed(1234 + layer + 1000 * rank)
+        Ks.append(torch.randn(B, Hkv, L, d, generator=g, device=dev, dtype=torch.float32).to(dtype))
+        Vs.append(torch.randn(B, Hkv, L, d, generator=g, device=dev, dtype=torch.float32).to(dtype))
+        # query_states as HF hands it over: a [B,L,Hq,d] buffer viewed as [B,Hq,L,d]; only the window is read
+        qbuf = torch.zeros(B, L, Hq, d, device=dev, dtype=dtype)
+        qbuf[:, L - w:] = torch.randn(B, w, Hq, d, generator=g, device=dev, dtype=torch.float32).to(dtype)
+        Qs.append(qbuf.transpose(1, 2))
+        if wl["method"] == "pyramidkv":
+            cl = PyramidKVCluster(num_hidden_layers=nl, window_size=w, max_capacity_prompt=wl["cap"],
+                                  kernel_size=wl["kernel"], pooling=wl["pooling"], layer_idx=layer)
+        else:
+            cl = SnapKVCluster(w, wl["cap"], wl["kernel"], wl["pooling"])
+        cl.score_impl = impl
+        clusters.append(cl)
+    groups = Hq // Hkv
+
+    def step():
+        out = None
+        for layer in range(nl):
+            out = clusters[layer].update_kv(Ks[layer], Qs[layer], Vs[layer], None, groups)
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: device-resident, optionally replayed as one CUDA graph per step ------------------
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    graph = None
+    if not args.no_graph:
+        graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            step()
+            with torch.cuda.graph(graph, stream=side):
+                graph_out = step()
+        torch.cuda.current_stream().wait_stream(side)
+        for _ in range(2):
+            graph.replay()
+        torch.cuda.synchronize()
+    run_step = graph.replay if graph is not None else step
+
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    launches0 = _native.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        run_step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = _native.launch_count() - launches0
+    if graph is not None:  # graph replays do not pass through the library: count what was captured
+        l0 = _native.launch_count(); step(); launches = (_native.launch_count() - l0) * args.steps
+        torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = world * B * L / (ms_per_step * 1e-3)
+
+    # ---- phase split inside a timed region (CUDA events around each C-ABI call, eager launches) ----
+    phase = {"scores": [], "select": [], "gather": []}
+    ev = []
+    for _ in range(max(1, min(args.steps, 3))):
+        for layer in range(nl):
+            cl = clusters[layer]
+            n_keep = kept_rows(wl, layer) - w
+            marks = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            marks[0].record()
+            sc = _native.window_scores(Qs[layer], Ks[layer], w, "sum", impl)
+            marks[1].record()
+            idx, _, _ = _native.pool_topk(sc, wl["kernel"], wl["pooling"], n_keep)
+            marks[2].record()
+            _native.gather_dense(Ks[layer], Vs[layer], idx, Hq, n_keep, w)
+            marks[3].record()
+            ev.append((layer, marks))
+    torch.cuda.synchronize()
+    per_layer = {k: [[] for _ in range(nl)] for k in phase}
+    for layer, m in ev:
+        per_layer["scores"][layer].append(m[0].elapsed_time(m[1]))
+        per_layer["select"][layer].append(m[1].elapsed_time(m[2]))
+        per_layer["gather"][layer].append(m[2].elapsed_time(m[3]))
+    tot = {k: sum(statistics.mean(x) for x in per_layer[k]) for k in per_layer}  # ms per step
+    dominant = max(tot, key=tot.get)
+    sb = sum(alg_bytes_layer(wl, l)[0] for l in range(nl))
+    gb = sum(alg_bytes_layer(wl, l)[1] for l in range(nl))
+    alg = {"scores": sb, "select": 0, "gather": gb}
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    dom_bytes_per_launch = alg[dominant] / nl if dominant != "select" else (sb + gb) / nl
+    dom_ms = tot[dominant] / nl
+    achieved = dom_bytes_per_launch / (dom_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": {"scores": "window_scores (stats+scores passes)", "select": "pool_topk",
+                                           "gather": "gather_rows"}[dominant],
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src, "bytes_per_launch": dom_bytes_per_launch, "ms_per_launch": dom_ms,
+                "phase_ms_per_step": tot,
+                "step_frac_of_hbm_roofline": (sb + gb) / (ms_per_step * 1e-3) / 1e9 / peak}
+
+    # ---- e2e: host buffers -> compressed host buffers --------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        hc = HostCompressor(clusters, groups, dev)
+        hK = [k.cpu().pin_memory() for k in Ks]
+        hV = [v.cpu().pin_memory() for v in Vs]
+        hQ = [q[:, :, L - w:, :].contiguous().cpu().pin_memory() for q in Qs]   # the only rows the path reads
+        hc.run(hK, hQ, hV, L)                                                 # warm-up (allocates pinned outputs)
+        hc.run(hK, hQ, hV, L)
+        barrier()
+        n_e2e = max(1, min(args.steps, 3))
+        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(n_e2e):
+            hc.run(hK, hQ, hV, L)
+        t1.record()
+        barrier()
+        tt = torch.tensor([t0.elapsed_time(t1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_ms = float(tt.item()) / n_e2e
+        e2e = {"value": world * B * L / (e2e_ms * 1e-3), "unit": "tokens/s", "ms_per_step": e2e_ms,
+               "h2d_bytes_per_step": hc.h2d_bytes, "d2h_bytes_per_step": hc.d2h_bytes, "steps": n_e2e}
+        del hK, hV, hQ
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            n = wl["layers"]
+            sample = sorted(set([0, n // 2, n - 1]))
+            v, per_l, cores = cpu_reference(wl, sample)
+            cpu = {"value": v, "unit": "tokens/s", "cores": cores, "kind": "port",
+                   "sample": f"oracle/kvc_oracle.py on layers {sample} of {n} at full L={L} "
+                             f"({per_l * 1e3:.0f} ms/layer) x {n} layers"}
+        line = {
+            "metric": "kv_tokens_compressed_per_s", "value": value, "unit": "tokens/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": wl["dtype"], "data": "synthetic",
+            "config": dict(config_of(args.workload, wl, world), score_impl=args.score_impl,
+                           cuda_graph=graph is not None),
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="pyramidkv_llama3_8b_32k", choices=sorted(WORKLOADS))
+    ap.add_argument("--score-impl", default="auto", choices=["auto", "mma", "tc"])
+    ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl)
+    else:
+        run_ours(args, wl)
+
+
+if __name__ == "__main__":
+    main()

@@ -52,6 +52,8 @@ enum {
 int kvc_version(void);
 /* Thread-local description of the last non-zero status returned on this thread. */
 const char* kvc_last_error(void);
+/* Number of kernels this library has launched in this process (monotonic; used by bench.py). */
+uint64_t kvc_launch_count(void);
 /* Number of SMs of the current device (grids are sized in multiples of it). */
 int kvc_sm_count(int* out_sms);
 

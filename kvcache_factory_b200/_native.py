@@ -29,6 +29,7 @@ _i64, _p, _i = c_int64, c_void_p, c_int
 _SIGNATURES = {
     "kvc_version": (c_int, []),
     "kvc_last_error": (c_char_p, []),
+    "kvc_launch_count": (ctypes.c_uint64, []),
     "kvc_sm_count": (c_int, [POINTER(c_int)]),
     "kvc_window_scores_workspace_bytes": (c_size_t, [_i] * 6),
     "kvc_window_scores": (c_int, [_p, _i64, _i64, _i64, _p, _i64, _i64, _i64, _i, _i, _i, _i, _i, _i, _i, _i, _p,
@@ -126,22 +127,32 @@ def _rowmajor_last(t: torch.Tensor, align_elems: int) -> torch.Tensor:
 # op wrappers
 # ------------------------------------------------------------------------------------------------
 def window_scores(query_states: torch.Tensor, key_states: torch.Tensor, window_size: int,
-                  reduce: str = "sum", impl: int = IMPL_AUTO) -> torch.Tensor:
-    """[B,Hq,L-w] scores of every non-window key under the last ``window_size`` queries."""
+                  reduce: str = "sum", impl: int = IMPL_AUTO, seq_len: int = None) -> torch.Tensor:
+    """[B,Hq,L-w] scores of every non-window key under the last ``window_size`` queries.
+
+    ``query_states`` is ``[B,Hq,L,d]`` or, with ``seq_len=L``, only its last ``window_size`` rows
+    ``[B,Hq,w,d]`` (the C ABI addresses row L-w+i of the logical tensor, so the base pointer is
+    simply moved back by L-w rows; nothing outside the window is ever dereferenced).
+    """
     dev = _require_cuda(query_states, key_states)
-    B, Hq, L, d = query_states.shape
-    Hkv = key_states.shape[1]
+    B, Hq, Lq, d = query_states.shape
+    Hkv, L = key_states.shape[1], key_states.shape[2]
     code = dtype_code(key_states.dtype)
     if query_states.dtype != key_states.dtype:
         raise TypeError("query and key dtypes differ")
     q = _rowmajor_last(query_states, 2)
     k = _rowmajor_last(key_states, 8)
+    q_ptr = q.data_ptr()
+    if Lq != L:
+        if not (seq_len == L and Lq == window_size):
+            raise ValueError(f"query_states has {Lq} rows, key_states {L}")
+        q_ptr -= (L - window_size) * q.stride(2) * q.element_size()
     out = torch.empty((B, Hq, L - window_size), dtype=key_states.dtype, device=dev)
     with torch.cuda.device(dev):
         ws_bytes = lib().kvc_window_scores_workspace_bytes(B, Hq, Hkv, L, d, window_size)
         ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=dev)
         _check("kvc_window_scores", lib().kvc_window_scores(
-            q.data_ptr(), q.stride(0), q.stride(1), q.stride(2),
+            q_ptr, q.stride(0), q.stride(1), q.stride(2),
             k.data_ptr(), k.stride(0), k.stride(1), k.stride(2),
             B, Hq, Hkv, L, d, window_size, code, REDUCE_MEAN if reduce == "mean" else REDUCE_SUM,
             out.data_ptr(), ws.data_ptr(), ws.numel(), impl, _stream(dev)))
@@ -281,6 +292,11 @@ def update_flatten_view(cache: torch.Tensor, state: torch.Tensor, headlens: torc
             out.data_ptr(), cache.data_ptr(), state.data_ptr(), headlens.data_ptr(), cu_headlens.data_ptr(),
             H, d, cache.element_size(), total, _stream(dev)))
     return out
+
+
+def launch_count() -> int:
+    """Kernels launched by libkvc_b200 in this process so far."""
+    return int(lib().kvc_launch_count())
 
 
 def sm_count() -> int:

@@ -1,6 +1,6 @@
 // extern "C" surface of libkvc_b200.so (declared in include/kvc_b200.h): argument validation,
 // device check, dispatch to the sm_100a kernels.  No torch types cross this boundary.
-#include <mutex>
+#include <atomic>
 
 #include "common.cuh"
 
@@ -29,6 +29,10 @@ int h2o_scores(const void*, int64_t, int64_t, int64_t, const void*, int64_t, int
 size_t adakv_allocate_workspace_bytes(int H, int n);
 int adakv_allocate(const void*, const float*, int, int, int, int, float, int, int, int, int32_t*, int32_t*, int32_t*,
                    void*, size_t, cudaStream_t);
+
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+unsigned long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
 static thread_local char g_err[512] = "";
 char* last_error_buffer() { return g_err; }
@@ -85,6 +89,7 @@ extern "C" {
 
 int kvc_version(void) { return KVC_ABI_VERSION; }
 const char* kvc_last_error(void) { return last_error_buffer(); }
+uint64_t kvc_launch_count(void) { return (uint64_t)launch_count(); }
 
 int kvc_sm_count(int* out_sms) {
   KVC_REQUIRE(out_sms != nullptr, KVC_ERR_ARG, "out_sms is null");

@@ -30,7 +30,10 @@ int fail(int code, const char* fmt, ...);
     if (!(cond)) return ::kvc::fail((code), __VA_ARGS__); \
   } while (0)
 
+void count_launch();  // bumps the counter behind kvc_launch_count()
+
 inline int launch_status(const char* what) {
+  count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail((int)e, "launch of %s failed: %s", what, cudaGetErrorString(e));
   return 0;

@@ -94,15 +94,39 @@ class _ScoredCluster:
         self.pooling = pooling
         self.merge = merge
 
+    def _n_keep(self, q_len: int):
+        """Non-window rows to keep for a prompt of q_len tokens, or None for the pass-through branch."""
+        if q_len < self.max_capacity_prompt:
+            return None
+        return self.max_capacity_prompt - self.window_size
+
+    def update_kv_window(self, key_states, query_window, value_states, num_key_value_groups, seq_len=None):
+        """``update_kv`` for callers that hold only the observation window of the queries.
+
+        ``query_window`` is ``[B,Hq,window_size,d]`` (the last ``window_size`` rows of
+        ``query_states``); everything else is as in ``update_kv``.  Used by the host-buffer path,
+        which then never has to move the other L-w query rows.
+        """
+        q_len = key_states.shape[-2] if seq_len is None else seq_len
+        assert key_states.shape[-2] == q_len and query_window.shape[-2] == self.window_size
+        _kv_heads(key_states, query_window, num_key_value_groups)
+        n_keep = self._n_keep(q_len)
+        if n_keep is None:
+            return key_states, value_states
+        return self._compress(key_states, query_window, value_states, n_keep, scorer=self._scorer,
+                              pooling=self.pooling if self._scorer == "window" else None, seq_len=q_len)
+
+    _scorer = "window"
+
     def _compress(self, key_states, query_states, value_states, n_keep: int, *, scorer: str,
-                  pooling) -> Tuple[torch.Tensor, torch.Tensor]:
+                  pooling, seq_len=None) -> Tuple[torch.Tensor, torch.Tensor]:
         _check_merge(self.merge)
         w = self.window_size
         Hq = query_states.shape[1]
         if scorer == "window":
             if pooling not in ("avgpool", "maxpool"):
                 raise ValueError("Pooling method not supported")
-            scores = N.window_scores(query_states, key_states, w, "sum", self.score_impl)
+            scores = N.window_scores(query_states, key_states, w, "sum", self.score_impl, seq_len=seq_len)
         elif scorer == "h2o":
             scores = N.h2o_scores(query_states, key_states, w)
         else:
@@ -158,6 +182,12 @@ class PyramidKVCluster(_ScoredCluster):
         return pyramid_budget(q_len, self.window_size, self.max_capacity_prompt, self.num_hidden_layers,
                               self.layer_idx, self.beta)
 
+    def _n_keep(self, q_len: int):
+        base = self.max_capacity_prompt - self.window_size
+        if q_len < self.max_capacity_prompt:
+            return None                                              # :218-219
+        return base if q_len < base * 2 else self.layer_budget(q_len)  # :220 / :252
+
     def update_kv(self, key_states, query_states, value_states, attention_mask, num_key_value_groups):
         assert key_states.shape[-2] == query_states.shape[-2]        # :200
         q_len = query_states.shape[-2]
@@ -174,6 +204,11 @@ class PyramidKVCluster(_ScoredCluster):
 
 class H2OKVCluster(_ScoredCluster):
     """Reference ``H2OKVCluster`` (``pyramidkv_utils.py:516-575``): all queries, no pooling."""
+
+    _scorer = "h2o"
+
+    def update_kv_window(self, *a, **k):
+        raise TypeError("H2O scores every query row; it has no window-only entry")
 
     def __init__(self, window_size=64, max_capacity_prompt=256 + 64, kernel_size=5, pooling='avgpool', merge=None):
         self._configure(window_size, max_capacity_prompt, kernel_size, pooling, merge)
@@ -194,6 +229,8 @@ class H2OKVCluster(_ScoredCluster):
 
 class StreamingLLMKVCluster(_ScoredCluster):
     """Reference ``StreamingLLMKVCluster`` (``pyramidkv_utils.py:578-620``): sink rows + window."""
+
+    _scorer = "none"
 
     def __init__(self, window_size=64, max_capacity_prompt=256 + 64, kernel_size=5, pooling='avgpool', merge=None):
         self._configure(window_size, max_capacity_prompt, kernel_size, pooling, merge)
