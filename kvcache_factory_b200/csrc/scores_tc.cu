@@ -20,10 +20,16 @@
 // window sum in fp32 -> dtype.
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace kvc {
 namespace tc {
+
+// ---- timing trace (KVC_TC_DEBUG & 4): clock64 stamps of CTA (0,0), read back by kvc_debug_trace ----
+__device__ long long g_trace[512];
+#define KVC_TRACE(slot) do { if ((p.dbg & 4) && (((p.dbg & 8) != 0) != kPass2) && blockIdx.x == 0 && blockIdx.y == 0) g_trace[(slot)] = clock64(); } while (0)
 
 constexpr int kTile = 128;                    // keys per tile
 constexpr int kD = 128;                       // head_dim
@@ -31,6 +37,7 @@ constexpr int kHalfBytes = kTile * 64 * 2;    // one [128 x 64] swizzled half: 1
 constexpr int kTileBytes = 2 * kHalfBytes;    // 32 KiB
 constexpr int kNumBuf = 4;                    // TMEM accumulator buffers (128 columns each)
 constexpr int kEpiWarps = 8;
+constexpr int kNumWG = kEpiWarps / 4;
 constexpr int kThreads = 32 * (2 + kEpiWarps);
 
 struct Params {
@@ -39,6 +46,7 @@ struct Params {
   int chunk_tiles, nchunks;
   float scale;
   int reduce_mean;
+  int dbg;         // KVC_TC_DEBUG bits: 4 = record the clock64 trace of CTA (0,0) for pass 2, 4|8 = for pass 1
   float2* stats;   // [units][nchunks][RB*128]
   uint16_t* out;   // [B,Hq,L-w]
 };
@@ -123,11 +131,11 @@ struct Smem {
   static constexpr int kQBytes = RB * kTileBytes;
   static constexpr int kKBytes = kStages * kTileBytes;
   static constexpr int kBarOff = kQBytes + kKBytes;                    // 8-byte barriers
-  static constexpr int kNumBars = 2 * kStages + 2 * kNumBuf;
+  static constexpr int kNumBars = 2 * kStages + 2 * kNumBuf + 1;
   static constexpr int kTmemPtrOff = kBarOff + kNumBars * 8;
   static constexpr int kCrowOff = (kTmemPtrOff + 4 + 15) & ~15;        // float[RB*128]
   static constexpr int kXstatOff = kCrowOff + RB * 128 * 4;            // float2[RB][2][128]
-  static constexpr int kTotal = kXstatOff + RB * 2 * 128 * 8;
+  static constexpr int kTotal = kXstatOff + RB * kNumWG * 128 * 8;
   static constexpr int kAlloc = kTotal + 1024;                          // slack for the 1024-B alignment
 };
 
@@ -150,6 +158,7 @@ window_score_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const Params 
   const int tile_begin = chunk * p.chunk_tiles;
   const int ntiles = min(tile_begin + p.chunk_tiles, tiles_total) - tile_begin;
   if (ntiles <= 0) return;
+  if (threadIdx.x == 0) KVC_TRACE(0);
   const int nq = RB == 1 ? p.groups * p.w : 128;  // query rows per row block that carry data (UMMA N in pass 2)
 
   const uint32_t q_s = base, k_s = base + SM::kQBytes, bar_s = base + SM::kBarOff;
@@ -161,10 +170,12 @@ window_score_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const Params 
   float* crow = reinterpret_cast<float*>(smem + SM::kCrowOff);
   float2* xstat = reinterpret_cast<float2*>(smem + SM::kXstatOff);
 
-  // ---- one-time setup -------------------------------------------------------------------------
+  // ---- one-time setup: barriers + TMEM, then the roles start; the K stream does not wait for Q ----
+  const uint32_t qbar = bar_s + 8u * (2 * S + 2 * kNumBuf);
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(kfull(s), 1); mbar_init(kempty(s), 1); }
     for (int i = 0; i < kNumBuf; ++i) { mbar_init(tfull(i), 1); mbar_init(tempty(i), 4); }
+    mbar_init(qbar, kEpiWarps * 32);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -173,39 +184,58 @@ window_score_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const Params 
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  // Q block(s) -> shared memory in the canonical K-major SWIZZLE_128B layout:
-  // byte(row, col) = half(col/64) * 16 KiB + row * 128 + ((col%64)/8 ^ row%8) * 16 + (col%8) * 2
-  for (int e = tid; e < RB * 128 * 16; e += kThreads) {
-    const int rg = e >> 4, c16 = e & 15;        // global stacked row, 16-byte chunk of the row
-    const int rb = rg >> 7, r = rg & 127;
-    const int hl = rg / W, i = rg % W;
-    int4 val = make_int4(0, 0, 0, 0);
-    if (hl < p.groups) {
-      const uint16_t* src = p.q + b * p.q_sb + (int64_t)(kvh * p.groups + hl) * p.q_sh +
-                            (int64_t)(nscore + i) * p.q_sl + c16 * 8;
-      val = *reinterpret_cast<const int4*>(src);
-    }
-    *reinterpret_cast<int4*>(smem + rb * kTileBytes + (c16 >> 3) * kHalfBytes + r * 128 + (((c16 & 7) ^ (r & 7)) << 4)) = val;
-  }
-  if constexpr (kPass2) {
-    // fold every chunk's (m, Z) of this unit into c_row = -M*log2e - log2 Z
-    for (int r = tid; r < RB * 128; r += kThreads) {
-      const float2* st = p.stats + (int64_t)unit * p.nchunks * (RB * 128) + r;
-      float M = -1e30f;
-      for (int c = 0; c < p.nchunks; ++c) M = fmaxf(M, st[(int64_t)c * (RB * 128)].x);
-      float Z = 0.f;
-      for (int c = 0; c < p.nchunks; ++c) {
-        const float2 s = st[(int64_t)c * (RB * 128)];
-        Z += s.y * fast_exp2((s.x - M) * kLog2e);
-      }
-      crow[r] = (r / W < p.groups) ? (-M * kLog2e - log2f(Z)) : -INFINITY;
-    }
-  }
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy Q writes -> visible to UMMA
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  if (threadIdx.x == 0) KVC_TRACE(1);
+
+  if (warp >= 2) {
+    // Epilogue warps stage the Q block(s) with cp.async (all 16-byte chunks in flight at once) in the
+    // canonical K-major SWIZZLE_128B layout:
+    //   byte(row, col) = half(col/64) * 16 KiB + row * 128 + ((col%64)/8 ^ row%8) * 16 + (col%8) * 2
+    const int et = tid - 64;
+#pragma unroll
+    for (int it = 0; it < (RB * 128 * 16 + kEpiWarps * 32 - 1) / (kEpiWarps * 32); ++it) {
+      const int e = et + it * (kEpiWarps * 32);
+      if (e >= RB * 128 * 16) break;
+      const int rg = e >> 4, c16 = e & 15;  // stacked query row, 16-byte chunk of the row
+      const int rb = rg >> 7, r = rg & 127;
+      const int hl = rg / W, i = rg % W;
+      const bool ok = hl < p.groups;
+      const uint16_t* src = p.q + b * p.q_sb + (int64_t)(kvh * p.groups + (ok ? hl : 0)) * p.q_sh +
+                            (int64_t)(nscore + i) * p.q_sl + c16 * 8;
+      const uint32_t dst = q_s + rb * kTileBytes + (c16 >> 3) * kHalfBytes + r * 128 + (((c16 & 7) ^ (r & 7)) << 4);
+      const int sz = ok ? 16 : 0;  // padding rows are zero-filled
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    if constexpr (kPass2) {
+      // fold every chunk's (m, Z) of this unit into c_row = -M*log2e - log2 Z (loads batched by 8)
+      for (int r = et; r < RB * 128; r += kEpiWarps * 32) {
+        const float2* st = p.stats + (int64_t)unit * p.nchunks * (RB * 128) + r;
+        float M = -1e30f, Z = 0.f;
+        for (int c0 = 0; c0 < p.nchunks; c0 += 8) {
+          float2 sv[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            sv[u] = c0 + u < p.nchunks ? st[(int64_t)(c0 + u) * (RB * 128)] : make_float2(-1e30f, 0.f);
+          float mx = M;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) mx = fmaxf(mx, sv[u].x);
+          Z *= fast_exp2((M - mx) * kLog2e);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) Z += sv[u].y * fast_exp2((sv[u].x - mx) * kLog2e);
+          M = mx;
+        }
+        crow[r] = (r / W < p.groups) ? (-M * kLog2e - log2f(Z)) : -INFINITY;
+      }
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy Q writes -> visible to UMMA
+    mbar_arrive(qbar);
+    asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");  // c_row visible to all epilogue warps
+  }
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -217,15 +247,20 @@ window_score_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const Params 
         const int key0 = (tile_begin + t) * kTile;
         tma_load_4d(k_s + s * kTileBytes, &tmap_k, kfull(s), 0, key0, kvh, b);
         tma_load_4d(k_s + s * kTileBytes + kHalfBytes, &tmap_k, kfull(s), 64, key0, kvh, b);
+        if (t < 32) KVC_TRACE(32 + t);
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
       const uint32_t idesc = instr_desc(T::kDtype == KVC_BF16 ? 1 : 0, 128, kPass2 ? nq : 128);
+      mbar_wait(qbar, 0);  // Q block(s) staged
+      KVC_TRACE(2);
+      tc_fence_after();
       for (int t = 0; t < ntiles; ++t) {
         const int s = t % S;
         mbar_wait(kfull(s), (t / S) & 1);
+        if (t < 32) KVC_TRACE(64 + t);
         tc_fence_after();
 #pragma unroll
         for (int rb = 0; rb < RB; ++rb) {
@@ -245,7 +280,7 @@ window_score_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const Params 
       }
     }
   } else {
-    // ===== epilogue warps: two groups of four, alternating accumulator buffers =====
+    // ===== epilogue warps: kNumWG groups of four warps take accumulator tiles round-robin =====
     const int wg = (warp - 2) >> 2;
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may read
     const int r_loc = quad * 32 + lane;        // pass 1: query row in block; pass 2: key in tile
@@ -253,10 +288,11 @@ window_score_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const Params 
 #pragma unroll
     for (int rb = 0; rb < RB; ++rb) { m_run[rb] = -1e30f; z_run[rb] = 0.f; }
 
-    for (int j = wg; j < ntiles * RB; j += 2) {
+    for (int j = wg; j < ntiles * RB; j += kNumWG) {
       const int t = j / RB, rb = j % RB, buf = j % kNumBuf;
       const int key0 = (tile_begin + t) * kTile;
       mbar_wait(tfull(buf), (j / kNumBuf) & 1);
+      if (warp == 2 + 4 * wg && lane == 0 && j < 32) KVC_TRACE(96 + j);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * 128;
 
@@ -266,75 +302,119 @@ window_score_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const Params 
         const int hl = rg / W, wi = rg % W;
         const bool needs_mask = key0 + kTile > nscore;
         const int last_key = min(p.L - 1, hl < p.groups ? nscore + wi : p.L - 1);  // last visible key of this row
+        // packed fp32x2 math (FMUL2 / FFMA2 / FADD2) halves the issue slots of the scale/exp chain
+        const float2 scale2 = make_float2(p.scale, p.scale);
         uint32_t r2[64];
+        {
+          // all four 32-column loads in flight, ONE wait, then the accumulator buffer goes straight back
+          uint32_t v[4][32];
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-          uint32_t v[32];
-          tmem_ld32(taddr + cc * 32, v);
+          for (int cc = 0; cc < 4; ++cc) tmem_ld32(taddr + cc * 32, v[cc]);
           tmem_ld_wait();
+          if (warp == 2 + 4 * wg && lane == 0 && j < 32) KVC_TRACE(160 + j);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty(buf));
+          // staged so that the 16 independent pack -> scale -> pack chains of a chunk interleave
 #pragma unroll
-          for (int pi = 0; pi < 16; ++pi) {
-            const uint32_t p1 = T::pack(__uint_as_float(v[2 * pi]), __uint_as_float(v[2 * pi + 1]));
-            uint32_t p2 = T::pack(T::lo(p1) * p.scale, T::hi(p1) * p.scale);
-            if (needs_mask) {
-              const int key = key0 + cc * 32 + 2 * pi;
-              if (key > last_key) p2 = (p2 & 0xffff0000u) | (T::kNegInfPair & 0xffffu);
-              if (key + 1 > last_key) p2 = (p2 & 0x0000ffffu) | (T::kNegInfPair & 0xffff0000u);
-            }
-            r2[cc * 16 + pi] = p2;
+          for (int cc = 0; cc < 4; ++cc) {
+            uint32_t p1[16];
+            float2 f[16];
+#pragma unroll
+            for (int pi = 0; pi < 16; ++pi)
+              p1[pi] = T::pack(__uint_as_float(v[cc][2 * pi]), __uint_as_float(v[cc][2 * pi + 1]));
+#pragma unroll
+            for (int pi = 0; pi < 16; ++pi) f[pi] = __fmul2_rn(make_float2(T::lo(p1[pi]), T::hi(p1[pi])), scale2);
+#pragma unroll
+            for (int pi = 0; pi < 16; ++pi) r2[cc * 16 + pi] = T::pack(f[pi].x, f[pi].y);
           }
         }
-        // accumulator drained: hand the TMEM buffer back before the exp work
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tempty(buf));
+        if (needs_mask) {  // only the tile(s) touching the window block / the ragged end
+#pragma unroll
+          for (int i = 0; i < 64; ++i) {
+            const int key = key0 + 2 * i;
+            if (key > last_key) r2[i] = (r2[i] & 0xffff0000u) | (T::kNegInfPair & 0xffffu);
+            if (key + 1 > last_key) r2[i] = (r2[i] & 0x0000ffffu) | (T::kNegInfPair & 0xffff0000u);
+          }
+        }
 
+        if (warp == 2 + 4 * wg && lane == 0 && j < 32) KVC_TRACE(192 + j);
         uint32_t pm = r2[0];
 #pragma unroll
         for (int i = 1; i < 64; ++i) pm = T::max2(pm, r2[i]);
         const float m_new = fmaxf(m_run[rb], fmaxf(T::lo(pm), T::hi(pm)));
-        float z0 = z_run[rb] * fast_exp2((m_run[rb] - m_new) * kLog2e), z1 = 0.f;
-        const float ml = -m_new * kLog2e;
+        const float2 ml2 = make_float2(-m_new * kLog2e, -m_new * kLog2e);
+        const float2 l2e2 = make_float2(kLog2e, kLog2e);
+        float2 zacc[4];
+        zacc[0] = make_float2(z_run[rb] * fast_exp2((m_run[rb] - m_new) * kLog2e), 0.f);
+        zacc[1] = zacc[2] = zacc[3] = make_float2(0.f, 0.f);
+        if (warp == 2 + 4 * wg && lane == 0 && j < 32) KVC_TRACE(224 + j);
 #pragma unroll
-        for (int i = 0; i < 64; ++i) {
-          z0 += fast_exp2(fmaf(T::lo(r2[i]), kLog2e, ml));
-          z1 += fast_exp2(fmaf(T::hi(r2[i]), kLog2e, ml));
+        for (int bt = 0; bt < 4; ++bt) {  // 16 pairs per batch: FFMA2s, then the 32 exps, then the adds
+          float2 a[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            a[i] = __ffma2_rn(make_float2(T::lo(r2[bt * 16 + i]), T::hi(r2[bt * 16 + i])), l2e2, ml2);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) a[i] = make_float2(fast_exp2(a[i].x), fast_exp2(a[i].y));
+#pragma unroll
+          for (int i = 0; i < 16; ++i) zacc[i & 3] = __fadd2_rn(zacc[i & 3], a[i]);
         }
+        const float2 z2 = __fadd2_rn(__fadd2_rn(zacc[0], zacc[1]), __fadd2_rn(zacc[2], zacc[3]));
         m_run[rb] = m_new;
-        z_run[rb] = z0 + z1;
+        if (warp == 2 + 4 * wg && lane == 0 && j < 32) KVC_TRACE(128 + j);
+        z_run[rb] = z2.x + z2.y;
       } else {
         // ---- scores: this thread owns one key, the columns are the stacked query rows ----
         constexpr int kHeadsPerBlk = 128 / W;
-        float acc[kHeadsPerBlk];
+        float2 acc[kHeadsPerBlk];
 #pragma unroll
-        for (int h = 0; h < kHeadsPerBlk; ++h) acc[h] = 0.f;
+        for (int h = 0; h < kHeadsPerBlk; ++h) acc[h] = make_float2(0.f, 0.f);
+        const float2 scale2 = make_float2(p.scale, p.scale);
+        const float2 l2e2 = make_float2(kLog2e, kLog2e);
         const float* cr = crow + rb * 128;
+        // All four 32-column chunks are processed: columns >= nq belong to padding rows whose
+        // c_row is -inf, so they contribute exp2(-inf) = 0 (and their heads are never stored).
+        uint32_t r2[64];
+        {
+          uint32_t v[4][32];
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-          if (cc * 32 < nq) {
-            uint32_t v[32];
-            tmem_ld32(taddr + cc * 32, v);
-            tmem_ld_wait();
-            if ((cc + 1) * 32 >= nq) {  // last chunk read: release the accumulator buffer
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(tempty(buf));
-            }
+          for (int cc = 0; cc < 4; ++cc) tmem_ld32(taddr + cc * 32, v[cc]);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty(buf));  // accumulator drained: release it before the exp work
 #pragma unroll
-            for (int q4 = 0; q4 < 8; ++q4) {
-              const float4 c4 = *reinterpret_cast<const float4*>(cr + cc * 32 + q4 * 4);
-              const float cs[4] = {c4.x, c4.y, c4.z, c4.w};
+          for (int cc = 0; cc < 4; ++cc) {
+            uint32_t p1[16];
+            float2 f[16];
 #pragma unroll
-              for (int h2 = 0; h2 < 2; ++h2) {
-                const int col = cc * 32 + q4 * 4 + h2 * 2;
-                const uint32_t p1 = T::pack(__uint_as_float(v[q4 * 4 + h2 * 2]), __uint_as_float(v[q4 * 4 + h2 * 2 + 1]));
-                const uint32_t p2 = T::pack(T::lo(p1) * p.scale, T::hi(p1) * p.scale);
-                const float e0 = fast_exp2(fmaf(T::lo(p2), kLog2e, cs[h2 * 2]));
-                const float e1 = fast_exp2(fmaf(T::hi(p2), kLog2e, cs[h2 * 2 + 1]));
-                const uint32_t pp = T::pack(e0, e1);
-                acc[col / W] += T::lo(pp) + T::hi(pp);
-              }
-            }
+            for (int pi = 0; pi < 16; ++pi)
+              p1[pi] = T::pack(__uint_as_float(v[cc][2 * pi]), __uint_as_float(v[cc][2 * pi + 1]));
+#pragma unroll
+            for (int pi = 0; pi < 16; ++pi) f[pi] = __fmul2_rn(make_float2(T::lo(p1[pi]), T::hi(p1[pi])), scale2);
+#pragma unroll
+            for (int pi = 0; pi < 16; ++pi) r2[cc * 16 + pi] = T::pack(f[pi].x, f[pi].y);
+          }
+        }
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {  // 16 pairs per batch: FFMA2s, 32 exps, packs, adds
+          float2 a[16];
+#pragma unroll
+          for (int q4 = 0; q4 < 8; ++q4) {
+            const float4 c4 = *reinterpret_cast<const float4*>(cr + cc * 32 + q4 * 4);
+            a[2 * q4] = __ffma2_rn(make_float2(T::lo(r2[cc * 16 + 2 * q4]), T::hi(r2[cc * 16 + 2 * q4])), l2e2,
+                                   make_float2(c4.x, c4.y));
+            a[2 * q4 + 1] = __ffma2_rn(make_float2(T::lo(r2[cc * 16 + 2 * q4 + 1]), T::hi(r2[cc * 16 + 2 * q4 + 1])),
+                                       l2e2, make_float2(c4.z, c4.w));
+          }
+          uint32_t pp[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pp[i] = T::pack(fast_exp2(a[i].x), fast_exp2(a[i].y));
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int col = cc * 32 + 2 * i;
+            acc[col / W] = __fadd2_rn(acc[col / W], make_float2(T::lo(pp[i]), T::hi(pp[i])));
           }
         }
         const int key = key0 + r_loc;
@@ -343,7 +423,7 @@ window_score_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const Params 
           for (int h = 0; h < kHeadsPerBlk; ++h) {
             const int head = rb * kHeadsPerBlk + h;
             if (head < p.groups) {
-              float s = acc[h];
+              float s = acc[h].x + acc[h].y;
               if (p.reduce_mean) s = s / (float)p.w;
               p.out[((int64_t)b * p.Hq + kvh * p.groups + head) * nscore + key] = T::round1(s);
             }
@@ -353,18 +433,24 @@ window_score_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const Params 
     }
     if constexpr (!kPass2) {
 #pragma unroll
-      for (int rb = 0; rb < RB; ++rb) xstat[(rb * 2 + wg) * 128 + r_loc] = make_float2(m_run[rb], z_run[rb]);
+      for (int rb = 0; rb < RB; ++rb) xstat[(rb * kNumWG + wg) * 128 + r_loc] = make_float2(m_run[rb], z_run[rb]);
     }
   }
 
+  if (threadIdx.x == 0) KVC_TRACE(3);
   tc_fence_before();
   __syncthreads();
   if constexpr (!kPass2) {
     for (int r = tid; r < RB * 128; r += kThreads) {
       const int rb = r >> 7, rl = r & 127;
-      const float2 a = xstat[(rb * 2 + 0) * 128 + rl], c = xstat[(rb * 2 + 1) * 128 + rl];
-      const float mn = fmaxf(a.x, c.x);
-      const float z = a.y * fast_exp2((a.x - mn) * kLog2e) + c.y * fast_exp2((c.x - mn) * kLog2e);
+      float mn = -1e30f, z = 0.f;
+#pragma unroll
+      for (int g = 0; g < kNumWG; ++g) mn = fmaxf(mn, xstat[(rb * kNumWG + g) * 128 + rl].x);
+#pragma unroll
+      for (int g = 0; g < kNumWG; ++g) {
+        const float2 a = xstat[(rb * kNumWG + g) * 128 + rl];
+        z += a.y * fast_exp2((a.x - mn) * kLog2e);
+      }
       p.stats[((int64_t)unit * p.nchunks + chunk) * (RB * 128) + r] = make_float2(mn, z);
     }
   }
@@ -486,6 +572,7 @@ int window_scores_tc(const void* q, int64_t q_sb, int64_t q_sh, int64_t q_sl, co
   sp.chunk_tiles = pl.chunk_tiles; sp.nchunks = pl.nchunks;
   sp.scale = 1.0f / sqrtf((float)d);
   sp.reduce_mean = reduce == KVC_REDUCE_MEAN;
+  { const char* e = getenv("KVC_TC_DEBUG"); sp.dbg = e ? atoi(e) : 0; }
   sp.stats = (float2*)workspace;
   sp.out = (uint16_t*)out_scores;
   const int units = B * Hkv;
@@ -495,3 +582,8 @@ int window_scores_tc(const void* q, int64_t q_sb, int64_t q_sh, int64_t q_sl, co
 }
 
 }  // namespace kvc
+
+// Debug only: copy the clock64 trace of CTA (0,0) of the last traced launch (KVC_TC_DEBUG & 4).
+extern "C" int kvc_debug_trace(long long* out_host_512) {
+  return (int)cudaMemcpyFromSymbol(out_host_512, kvc::tc::g_trace, 512 * sizeof(long long));
+}

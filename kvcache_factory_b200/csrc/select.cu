@@ -241,6 +241,10 @@ pool_topk_kernel(const uint16_t* __restrict__ scores, int n, int kernel_size, in
   }
 }
 
+int pool_topk_cluster(const void* scores, int rows, int n, int dtype, int kernel_size, int pool, int k,
+                      const int32_t* k_per_row, int32_t* out_idx, int64_t idx_stride, void* out_pooled,
+                      float* out_sums, cudaStream_t stream);  // select_cluster.cu; returns 1 when not applicable
+
 static int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
 size_t pool_topk_workspace_bytes(int rows, int n, int k) {
@@ -255,6 +259,11 @@ int pool_topk(const void* scores, int rows, int n, int dtype, int kernel_size, i
               void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   KVC_REQUIRE(workspace_bytes >= pool_topk_workspace_bytes(rows, n, k), KVC_ERR_WORKSPACE,
               "pool_topk workspace: have %zu need %zu", workspace_bytes, pool_topk_workspace_bytes(rows, n, k));
+  {
+    const int rc = pool_topk_cluster(scores, rows, n, dtype, kernel_size, pool, k, k_per_row, out_idx, idx_stride,
+                                     out_pooled, out_sums, stream);
+    if (rc != 1) return rc;  // 1 = shape outside the cluster kernel: fall through to the one-CTA-per-row kernel
+  }
   const int kpad = next_pow2(k > 1 ? k : 1);
   const size_t keys_bytes = ((size_t)rows * n * 2 + 255) & ~(size_t)255;
   uint16_t* keys = (uint16_t*)workspace;

@@ -1,0 +1,390 @@
+// Pool + top-k select, cluster version: one thread-block CLUSTER per score row, so a handful of rows
+// (B*Hq = 32 at batch 1) still occupies most of the chip.
+//
+// CTA c of the C-CTA cluster owns the contiguous slice [c*SL, (c+1)*SL) of the row (SL = 256*E).
+//   1. stage slice + pooling halo in shared memory (coalesced), pool, keep 16-bit keys in registers
+//   2. exact k-th largest key by a 2-round radix select on 8-bit digits: warp-private histograms
+//      filled with match.any-aggregated updates (no atomics), summed per CTA, exchanged through
+//      distributed shared memory (one cluster barrier per round)
+//   3. winners are compacted in index order (block scan + per-CTA bases exchanged through DSMEM) and
+//      written straight into CTA 0's shared memory with st.shared::cluster
+//   4. CTA 0 orders them with a stable 2-pass LSD radix sort (O(k), ranks from match.any) and emits
+//      indices by descending value, ascending position among equal values (torch.topk sorted=True,
+//      deterministic on ties)
+// Rows longer than 16 * 8192 scores or k > 8192 use the one-CTA-per-row kernel in select.cu.
+#include "common.cuh"
+
+namespace kvc {
+namespace cl {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kMaxK = 8192;
+constexpr int kHalo = 3;  // pooling kernels up to 7 taps
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_size() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_rank(const void* local, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(local)), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ uint32_t ld_cluster_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ float ld_cluster_f32(uint32_t a) { float v; asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void st_cluster_u32(uint32_t a, uint32_t v) { asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void st_cluster_u16(uint32_t a, uint16_t v) { asm volatile("st.shared::cluster.u16 [%0], %1;" ::"r"(a), "h"(v) : "memory"); }
+
+struct Shared {
+  int whist[kWarps][260];   // warp-private digit counters (256 digits + trash bin)
+  int hist[2][256];         // this CTA's per-round histograms, read by the whole cluster
+  int warp_tmp[kWarps];
+  float fsum[kWarps];
+  int totals[2];            // selected-above / equal-to-threshold counts of this CTA
+  float psum[2];            // partial sums (selected, all) of this CTA
+  int sel_digit, sel_above; // result of the per-round threshold search
+};
+
+// Exclusive block scan of one int per thread.
+__device__ __forceinline__ int block_scan_excl(int v, int* warp_tmp, int& total) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  __syncthreads();  // warp_tmp free to overwrite
+  if (lane == 31) warp_tmp[wid] = inc;
+  __syncthreads();
+  int base = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < kWarps; ++w) {
+    const int x = warp_tmp[w];
+    if (w < wid) base += x;
+    tot += x;
+  }
+  total = tot;
+  return base + inc - v;
+}
+
+__device__ __forceinline__ float block_sum_f(float v, float* tmp) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if (lane == 0) tmp[wid] = v;
+  __syncthreads();
+  float r = 0.f;
+#pragma unroll
+  for (int w = 0; w < kWarps; ++w) r += tmp[w];
+  return r;
+}
+
+// Add one occurrence of `digit` per participating lane to this warp's private histogram and return
+// how many same-digit occurrences this warp had counted before this lane (stable rank).
+__device__ __forceinline__ int warp_count_digit(int* wh, int digit, int lane) {
+  const unsigned peers = __match_any_sync(0xffffffffu, digit);
+  const int leader = __ffs(peers) - 1;
+  int old = 0;
+  if (lane == leader) { old = wh[digit]; wh[digit] = old + __popc(peers); }
+  old = __shfl_sync(0xffffffffu, old, leader);
+  return old + __popc(peers & ((1u << lane) - 1u));
+}
+
+// Sum the cluster's per-CTA histograms (round r) and find the digit at which the descending
+// running count reaches krem.  Every CTA computes the same answer.  256 threads <-> 256 digits.
+__device__ __forceinline__ void cluster_threshold(Shared& sh, int round, int krem, uint32_t csize, int& digit, int& above) {
+  const int tid = threadIdx.x;
+  const int d = 255 - tid;  // thread t looks at digit 255-t so that an ascending scan walks down from the top
+  int cnt = 0;
+  for (uint32_t c = 0; c < csize; ++c) cnt += (int)ld_cluster_u32(map_to_rank(&sh.hist[round][d], c));
+  int total;
+  const int ex = block_scan_excl(cnt, sh.warp_tmp, total);
+  if (ex < krem && ex + cnt >= krem) { sh.sel_digit = d; sh.sel_above = ex; }
+  __syncthreads();
+  digit = sh.sel_digit;
+  above = sh.sel_above;
+}
+
+template <typename T, int E, int POOL>
+__global__ void __launch_bounds__(kThreads)
+topk_cluster_kernel(const uint16_t* __restrict__ scores, int n, int kernel_size, int k_fixed,
+                    const int32_t* __restrict__ k_per_row, int32_t* __restrict__ out_idx, int64_t idx_stride,
+                    uint16_t* __restrict__ out_pooled, float* __restrict__ out_sums) {
+  constexpr int SL = kThreads * E;          // slice length
+  constexpr int ST = E + 2;                 // staged chunk stride (u16): (E+2)/2 words is odd -> no bank conflicts
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Shared& sh = *reinterpret_cast<Shared*>(smem_raw);
+  unsigned char* dyn = smem_raw + ((sizeof(Shared) + 15) & ~15);
+  uint16_t* stage = reinterpret_cast<uint16_t*>(dyn);   // phase 1-2
+  // phase 3-4 (CTA 0 only, written remotely): keys/indices ping-pong
+  uint16_t* skey[2] = {reinterpret_cast<uint16_t*>(dyn), reinterpret_cast<uint16_t*>(dyn) + kMaxK};
+  uint32_t* sidx[2] = {reinterpret_cast<uint32_t*>(dyn + 4 * kMaxK), reinterpret_cast<uint32_t*>(dyn + 4 * kMaxK) + kMaxK};
+
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const uint32_t crank = cluster_rank(), csize = cluster_size();
+  const int row = blockIdx.y;
+  const uint16_t* srow = scores + (int64_t)row * n;
+  int k = k_per_row ? k_per_row[row] : k_fixed;
+  k = min(max(k, 0), n);
+  const int radius = POOL == KVC_POOL_NONE ? 0 : kernel_size / 2;
+  const int s0 = (int)crank * SL;
+
+  // ---- 1. stage [s0-kHalo, s0+SL+kHalo) and pool ------------------------------------------------
+  for (int q = tid; q < SL + 2 * kHalo; q += kThreads) {
+    const int j = s0 - kHalo + q;
+    stage[q + 2 * (q / E)] = (j >= 0 && j < n) ? srow[j] : (uint16_t)0;
+  }
+  __syncthreads();
+  const int j0 = s0 + tid * E;
+  uint32_t keys[E];
+  float part_all = 0.f;
+  {
+    float f[E + 2 * kHalo];
+    uint32_t kk[E + 2 * kHalo];
+#pragma unroll
+    for (int i = 0; i < E + 2 * kHalo; ++i) {
+      const int q = tid * E + i, j = s0 - kHalo + q;
+      const uint16_t raw = stage[q + 2 * (q / E)];
+      const bool in = j >= 0 && j < n;
+      if (POOL == KVC_POOL_AVG) f[i] = in ? T::to_float(raw) : 0.f;
+      else kk[i] = in ? float16_bits_to_key(raw) : 0u;
+    }
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+      uint32_t bits;
+      if (POOL == KVC_POOL_AVG) {
+        float s = 0.f;  // ascending position, zero padding, divisor = kernel_size (ATen avg_pool)
+        if (radius >= 3) s += f[i];
+        if (radius >= 2) s += f[i + 1];
+        if (radius >= 1) s += f[i + 2];
+        s += f[i + 3];
+        if (radius >= 1) s += f[i + 4];
+        if (radius >= 2) s += f[i + 5];
+        if (radius >= 3) s += f[i + 6];
+        bits = T::round1(s / (float)kernel_size);
+        keys[i] = float16_bits_to_key(bits);
+      } else {
+        uint32_t best = kk[i + 3];
+        if (POOL == KVC_POOL_MAX) {
+          if (radius >= 1) best = max(best, max(kk[i + 2], kk[i + 4]));
+          if (radius >= 2) best = max(best, max(kk[i + 1], kk[i + 5]));
+          if (radius >= 3) best = max(best, max(kk[i], kk[i + 6]));
+        }
+        keys[i] = best;
+        bits = key_to_float16_bits(best);
+      }
+      if (j0 + i < n) {
+        part_all += T::to_float((uint16_t)bits);
+        if (out_pooled) out_pooled[(int64_t)row * n + j0 + i] = (uint16_t)bits;
+      } else {
+        keys[i] = 0u;
+      }
+    }
+  }
+  const int nvalid = max(0, min(E, n - j0));
+  const float sum_all_cta = out_sums ? block_sum_f(part_all, sh.fsum) : 0.f;
+  if (k == 0) {  // uniform over the cluster; nothing to select (AdaKV asks only for pooled scores / sums)
+    if (out_sums) {
+      if (tid == 0) sh.psum[1] = sum_all_cta;
+      cluster_sync();
+      if (crank == 0 && tid == 0) {
+        float a = 0.f;
+        for (uint32_t c = 0; c < csize; ++c) a += ld_cluster_f32(map_to_rank(&sh.psum[1], c));
+        out_sums[2 * row] = 0.f;
+        out_sums[2 * row + 1] = a;
+      }
+      cluster_sync();
+    }
+    return;
+  }
+
+  // ---- 2. radix select, two 8-bit rounds ---------------------------------------------------------
+  int* wh = sh.whist[wid];
+  uint32_t thr_key = 0;
+  int krem = k;
+#pragma unroll
+  for (int round = 0; round < 2; ++round) {
+    for (int i = lane; i < 260; i += 32) wh[i] = 0;
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+      const bool in = i < nvalid && (round == 0 || (keys[i] >> 8) == thr_key);
+      const int dgt = in ? (int)((round == 0 ? keys[i] >> 8 : keys[i]) & 255u) : 256 + (lane & 3);
+      warp_count_digit(wh, dgt, lane);
+      __syncwarp();
+    }
+    __syncthreads();
+    {
+      int s = 0;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) s += sh.whist[w][tid];
+      sh.hist[round][tid] = s;
+    }
+    cluster_sync();  // every CTA's hist[round] is complete and visible
+    int digit, above;
+    cluster_threshold(sh, round, krem, csize, digit, above);
+    thr_key = (thr_key << 8) | (uint32_t)digit;
+    krem -= above;
+  }
+  const int need_eq = krem, count_gt = k - krem;
+
+  // ---- 3. ordered compaction into CTA 0 -----------------------------------------------------------
+  int gt = 0, eq = 0;
+#pragma unroll
+  for (int i = 0; i < E; ++i) {
+    gt += (i < nvalid && keys[i] > thr_key);
+    eq += (i < nvalid && keys[i] == thr_key);
+  }
+  int total;
+  const int ex = block_scan_excl(gt | (eq << 16), sh.warp_tmp, total);
+  if (tid == 0) { sh.totals[0] = total & 0xffff; sh.totals[1] = (int)((uint32_t)total >> 16); }
+  cluster_sync();  // totals visible; also: every CTA is past its last read of `stage`, so CTA 0's buffers are free
+  int gbase = 0, ebase = 0;
+  for (uint32_t c = 0; c < crank; ++c) {
+    gbase += (int)ld_cluster_u32(map_to_rank(&sh.totals[0], c));
+    ebase += (int)ld_cluster_u32(map_to_rank(&sh.totals[1], c));
+  }
+  int gpos = gbase + (ex & 0xffff), epos = ebase + (int)((uint32_t)ex >> 16);
+  const uint32_t rkey = map_to_rank(skey[0], 0), ridx = map_to_rank(sidx[0], 0);
+  float part_top = 0.f;
+#pragma unroll
+  for (int i = 0; i < E; ++i) {
+    if (i < nvalid) {
+      int pos = -1;
+      if (keys[i] > thr_key) pos = gpos++;
+      else if (keys[i] == thr_key) { if (epos < need_eq) pos = count_gt + epos; ++epos; }
+      if (pos >= 0) {
+        st_cluster_u16(rkey + 2u * pos, (uint16_t)keys[i]);
+        st_cluster_u32(ridx + 4u * pos, (uint32_t)(j0 + i));
+        part_top += T::to_float((uint16_t)key_to_float16_bits(keys[i]));
+      }
+    }
+  }
+  if (out_sums) {
+    const float st = block_sum_f(part_top, sh.fsum);
+    if (tid == 0) { sh.psum[0] = st; sh.psum[1] = sum_all_cta; }
+  }
+  cluster_sync();  // all winners (and partial sums) have landed in / are readable by CTA 0
+
+  // ---- 4. CTA 0: stable LSD radix sort by descending key, emit -------------------------------------
+  if (crank == 0) {
+    if (out_sums && tid == 0) {
+      float a = 0.f, bsum = 0.f;
+      for (uint32_t c = 0; c < csize; ++c) {
+        a += ld_cluster_f32(map_to_rank(&sh.psum[0], c));
+        bsum += ld_cluster_f32(map_to_rank(&sh.psum[1], c));
+      }
+      out_sums[2 * row] = a;
+      out_sums[2 * row + 1] = bsum;
+    }
+    const int V = (k + kThreads - 1) / kThreads;          // slots per thread
+    const int per_warp = V * 32;                          // warp w owns elements [w*per_warp, (w+1)*per_warp)
+    int cur = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+      for (int i = lane; i < 260; i += 32) wh[i] = 0;
+      __syncthreads();
+      // count + stable rank inside this warp's run (kept in registers via re-computation below)
+      // pass A: per-warp digit totals
+      for (int v = 0; v < V; ++v) {
+        const int o = wid * per_warp + v * 32 + lane;
+        const int dgt = o < k ? 255 - (int)((skey[cur][o] >> (8 * pass)) & 255u) : 256 + (lane & 3);
+        warp_count_digit(wh, dgt, lane);
+        __syncwarp();
+      }
+      __syncthreads();
+      // digit bases: thread t <-> digit t; exclusive scan over digits of the per-digit totals
+      int wcount[kWarps];
+      int tot = 0;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) { wcount[w] = sh.whist[w][tid]; tot += wcount[w]; }
+      int total2;
+      int dbase = block_scan_excl(tot, sh.warp_tmp, total2);
+      // turn the per-warp counters into start offsets: whist[w][d] = dbase[d] + sum_{w'<w} count[w'][d]
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) { sh.whist[w][tid] = dbase; dbase += wcount[w]; }
+      __syncthreads();
+      // pass B: scatter in the same (warp, slot, lane) order
+      for (int v = 0; v < V; ++v) {
+        const int o = wid * per_warp + v * 32 + lane;
+        const bool in = o < k;
+        const uint16_t key = in ? skey[cur][o] : (uint16_t)0;
+        const uint32_t idx = in ? sidx[cur][o] : 0u;
+        const int dgt = in ? 255 - (int)((key >> (8 * pass)) & 255u) : 256 + (lane & 3);
+        const int dst = warp_count_digit(wh, dgt, lane);
+        if (in) { skey[cur ^ 1][dst] = key; sidx[cur ^ 1][dst] = idx; }
+        __syncwarp();
+      }
+      __syncthreads();
+      cur ^= 1;
+    }
+    for (int r = tid; r < k; r += kThreads) out_idx[(int64_t)row * idx_stride + r] = (int32_t)sidx[cur][r];
+  }
+  cluster_sync();  // keep every CTA's shared memory alive until CTA 0 has read the partial sums
+}
+
+template <typename T, int E, int POOL>
+static int launch(const void* scores, int rows, int n, int C, int kernel_size, int k, const int32_t* k_per_row,
+                  int32_t* out_idx, int64_t idx_stride, void* out_pooled, float* out_sums, cudaStream_t stream) {
+  auto kern = topk_cluster_kernel<T, E, POOL>;
+  const size_t stage_bytes = (size_t)(kThreads * E + 2 * kHalo + 2 * (kThreads + 2)) * 2;
+  const size_t sort_bytes = (size_t)kMaxK * 12;
+  const size_t smem = ((sizeof(Shared) + 15) & ~(size_t)15) + (stage_bytes > sort_bytes ? stage_bytes : sort_bytes);
+  KVC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (C > 8) KVC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(C, rows);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = C;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const uint16_t* sc = (const uint16_t*)scores;
+  uint16_t* op = (uint16_t*)out_pooled;
+  KVC_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, sc, n, kernel_size, k, k_per_row, out_idx, idx_stride, op, out_sums));
+  return launch_status("topk_cluster_kernel");
+}
+
+template <typename T, int POOL>
+static int dispatch_e(const void* scores, int rows, int n, int kernel_size, int k, const int32_t* k_per_row,
+                      int32_t* out_idx, int64_t idx_stride, void* out_pooled, float* out_sums, cudaStream_t stream) {
+  // slice = 256*E elements per CTA; small rows use one CTA, long rows up to 16 CTAs of 8192
+  if (n <= 1024) return launch<T, 4, POOL>(scores, rows, n, 1, kernel_size, k, k_per_row, out_idx, idx_stride, out_pooled, out_sums, stream);
+  if (n <= 4096) return launch<T, 8, POOL>(scores, rows, n, (n + 2047) / 2048, kernel_size, k, k_per_row, out_idx, idx_stride, out_pooled, out_sums, stream);
+  if (n <= 16384) return launch<T, 16, POOL>(scores, rows, n, n <= 8192 ? 2 : 4, kernel_size, k, k_per_row, out_idx, idx_stride, out_pooled, out_sums, stream);
+  int C = 4;
+  while (C * 8192 < n) C <<= 1;
+  return launch<T, 32, POOL>(scores, rows, n, C, kernel_size, k, k_per_row, out_idx, idx_stride, out_pooled, out_sums, stream);
+}
+
+template <typename T>
+static int dispatch_pool(int pool, const void* scores, int rows, int n, int kernel_size, int k, const int32_t* k_per_row,
+                         int32_t* out_idx, int64_t idx_stride, void* out_pooled, float* out_sums, cudaStream_t stream) {
+  if (pool == KVC_POOL_AVG) return dispatch_e<T, KVC_POOL_AVG>(scores, rows, n, kernel_size, k, k_per_row, out_idx, idx_stride, out_pooled, out_sums, stream);
+  if (pool == KVC_POOL_MAX) return dispatch_e<T, KVC_POOL_MAX>(scores, rows, n, kernel_size, k, k_per_row, out_idx, idx_stride, out_pooled, out_sums, stream);
+  return dispatch_e<T, KVC_POOL_NONE>(scores, rows, n, kernel_size, k, k_per_row, out_idx, idx_stride, out_pooled, out_sums, stream);
+}
+
+}  // namespace cl
+
+// Returns 1 when the shape is outside what the cluster kernel covers (caller falls back).
+int pool_topk_cluster(const void* scores, int rows, int n, int dtype, int kernel_size, int pool, int k,
+                      const int32_t* k_per_row, int32_t* out_idx, int64_t idx_stride, void* out_pooled, float* out_sums,
+                      cudaStream_t stream) {
+  if (k > cl::kMaxK || n > 16 * 8192 || (pool != KVC_POOL_NONE && kernel_size > 2 * cl::kHalo + 1) || rows > 65535)
+    return 1;
+  return dtype == KVC_BF16
+             ? cl::dispatch_pool<Bf16>(pool, scores, rows, n, kernel_size, k, k_per_row, out_idx, idx_stride, out_pooled, out_sums, stream)
+             : cl::dispatch_pool<Fp16>(pool, scores, rows, n, kernel_size, k, k_per_row, out_idx, idx_stride, out_pooled, out_sums, stream);
+}
+
+}  // namespace kvc
