@@ -230,13 +230,17 @@ def run_ours(args, wl):
         else:
             cl = SnapKVCluster(w, wl["cap"], wl["kernel"], wl["pooling"])
         cl.score_impl = impl
+        cl.async_tail = not args.sync_tail
         clusters.append(cl)
     groups = Hq // Hkv
+
+    from kvcache_factory_b200 import wait_for_compression
 
     def step():
         out = None
         for layer in range(nl):
             out = clusters[layer].update_kv(Ks[layer], Qs[layer], Vs[layer], None, groups)
+        wait_for_compression(dev)  # join the asynchronous select/gather tails: all work ends inside the step
         return out
 
     def barrier():
@@ -370,7 +374,8 @@ def run_ours(args, wl):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": wl["dtype"], "data": "synthetic",
             "config": dict(config_of(args.workload, wl, world), score_impl=args.score_impl,
-                           cuda_graph=graph is not None),
+                           cuda_graph=graph is not None,
+                           async_tail=not args.sync_tail),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
@@ -387,6 +392,7 @@ def main():
     ap.add_argument("--workload", default="pyramidkv_llama3_8b_32k", choices=sorted(WORKLOADS))
     ap.add_argument("--score-impl", default="auto", choices=["auto", "mma", "tc"])
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--sync-tail", action="store_true", help="keep select+gather on the caller's stream")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

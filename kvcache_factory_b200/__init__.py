@@ -20,10 +20,11 @@ from .pyramidkv_utils import (  # noqa: F401
     init_StreamingLLM,
     pyramid_budget,
     repeat_kv,
+    wait_for_compression,
 )
 
 __all__ = [
     "AdaKVCluster", "DynamicCacheSplitHeadFlatten", "H2OKVCluster", "PyramidKVCluster", "SnapKVCluster",
     "StreamingLLMKVCluster", "init_adakv", "init_H2O", "init_pyramidkv", "init_snapkv", "init_StreamingLLM",
-    "pyramid_budget", "repeat_kv",
+    "pyramid_budget", "repeat_kv", "wait_for_compression",
 ]

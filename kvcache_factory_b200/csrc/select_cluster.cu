@@ -1,11 +1,13 @@
 // Pool + top-k select, cluster version: one thread-block CLUSTER per score row, so a handful of rows
 // (B*Hq = 32 at batch 1) still occupies most of the chip.
 //
-// CTA c of the C-CTA cluster owns the contiguous slice [c*SL, (c+1)*SL) of the row (SL = 256*E).
+// CTA c of the C-CTA cluster owns the contiguous slice [c*SL, (c+1)*SL) of the row (SL = 1024*E).
 //   1. stage slice + pooling halo in shared memory (coalesced), pool, keep 16-bit keys in registers
-//   2. exact k-th largest key by a 2-round radix select on 8-bit digits: warp-private histograms
-//      filled with match.any-aggregated updates (no atomics), summed per CTA, exchanged through
-//      distributed shared memory (one cluster barrier per round)
+//   2. exact k-th largest key in at most two counting rounds over a DATA-ADAPTIVE binning: the row's
+//      key range [kmin, kmax] is split into <= 256 bins of 2^sh keys, the threshold bin is located,
+//      then (if sh > 0) its 2^sh <= 256 keys are resolved.  Counting uses warp-private shared-memory
+//      histograms (plain atomics: the adaptive bins spread the keys, so same-address conflicts are
+//      rare); per-CTA histograms are exchanged through distributed shared memory.
 //   3. winners are compacted in index order (block scan + per-CTA bases exchanged through DSMEM) and
 //      written straight into CTA 0's shared memory with st.shared::cluster
 //   4. CTA 0 orders them with a stable 2-pass LSD radix sort (O(k), ranks from match.any) and emits
@@ -17,7 +19,7 @@
 namespace kvc {
 namespace cl {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 1024;
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxK = 8192;
 constexpr int kHalo = 3;  // pooling kernels up to 7 taps
@@ -39,16 +41,18 @@ __device__ __forceinline__ void st_cluster_u32(uint32_t a, uint32_t v) { asm vol
 __device__ __forceinline__ void st_cluster_u16(uint32_t a, uint16_t v) { asm volatile("st.shared::cluster.u16 [%0], %1;" ::"r"(a), "h"(v) : "memory"); }
 
 struct Shared {
-  int whist[kWarps][260];   // warp-private digit counters (256 digits + trash bin)
+  int whist[kWarps][256];   // warp-private counters (select rounds: bins; sort: digit offsets)
   int hist[2][256];         // this CTA's per-round histograms, read by the whole cluster
   int warp_tmp[kWarps];
+  int warp_tmp2[kWarps];
   float fsum[kWarps];
+  int mm[2];                // min / max key of this CTA's slice
   int totals[2];            // selected-above / equal-to-threshold counts of this CTA
   float psum[2];            // partial sums (selected, all) of this CTA
   int sel_digit, sel_above; // result of the per-round threshold search
 };
 
-// Exclusive block scan of one int per thread.
+// Exclusive block scan of one int per thread (1024 threads).
 __device__ __forceinline__ int block_scan_excl(int v, int* warp_tmp, int& total) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   int inc = v;
@@ -60,14 +64,15 @@ __device__ __forceinline__ int block_scan_excl(int v, int* warp_tmp, int& total)
   __syncthreads();  // warp_tmp free to overwrite
   if (lane == 31) warp_tmp[wid] = inc;
   __syncthreads();
-  int base = 0, tot = 0;
+  const int mine = warp_tmp[lane];  // kWarps == 32: lane l holds warp l's total
+  int pre = mine;
 #pragma unroll
-  for (int w = 0; w < kWarps; ++w) {
-    const int x = warp_tmp[w];
-    if (w < wid) base += x;
-    tot += x;
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, pre, o);
+    if (lane >= o) pre += t;
   }
-  total = tot;
+  total = __shfl_sync(0xffffffffu, pre, 31);
+  const int base = __shfl_sync(0xffffffffu, pre - mine, wid);
   return base + inc - v;
 }
 
@@ -78,36 +83,57 @@ __device__ __forceinline__ float block_sum_f(float v, float* tmp) {
   __syncthreads();
   if (lane == 0) tmp[wid] = v;
   __syncthreads();
-  float r = 0.f;
+  float r = tmp[lane];
 #pragma unroll
-  for (int w = 0; w < kWarps; ++w) r += tmp[w];
+  for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
   return r;
 }
 
-// Add one occurrence of `digit` per participating lane to this warp's private histogram and return
-// how many same-digit occurrences this warp had counted before this lane (stable rank).
-__device__ __forceinline__ int warp_count_digit(int* wh, int digit, int lane) {
+// Stable rank: add one occurrence of `digit` per lane to this warp's counters and return the
+// counter value seen by this lane as if lanes were processed in lane order.
+__device__ __forceinline__ int warp_rank_digit(int* wh, int digit, int lane) {
   const unsigned peers = __match_any_sync(0xffffffffu, digit);
-  const int leader = __ffs(peers) - 1;
-  int old = 0;
-  if (lane == leader) { old = wh[digit]; wh[digit] = old + __popc(peers); }
-  old = __shfl_sync(0xffffffffu, old, leader);
-  return old + __popc(peers & ((1u << lane) - 1u));
+  const int old = wh[digit];
+  __syncwarp();
+  const int rank = __popc(peers & ((1u << lane) - 1u));
+  if (rank == 0) wh[digit] = old + __popc(peers);  // lowest peer lane updates the counter
+  __syncwarp();
+  return old + rank;
 }
 
-// Sum the cluster's per-CTA histograms (round r) and find the digit at which the descending
-// running count reaches krem.  Every CTA computes the same answer.  256 threads <-> 256 digits.
+// Sum the cluster's per-CTA histograms of `round` and find the bin at which the descending running
+// count reaches krem.  Every CTA computes the same answer.  Threads 0..255 <-> bins 255..0.
 __device__ __forceinline__ void cluster_threshold(Shared& sh, int round, int krem, uint32_t csize, int& digit, int& above) {
   const int tid = threadIdx.x;
-  const int d = 255 - tid;  // thread t looks at digit 255-t so that an ascending scan walks down from the top
+  const int d = 255 - tid;
   int cnt = 0;
-  for (uint32_t c = 0; c < csize; ++c) cnt += (int)ld_cluster_u32(map_to_rank(&sh.hist[round][d], c));
+  if (tid < 256)
+    for (uint32_t c = 0; c < csize; ++c) cnt += (int)ld_cluster_u32(map_to_rank(&sh.hist[round][d], c));
   int total;
   const int ex = block_scan_excl(cnt, sh.warp_tmp, total);
-  if (ex < krem && ex + cnt >= krem) { sh.sel_digit = d; sh.sel_above = ex; }
+  if (tid < 256 && ex < krem && ex + cnt >= krem) { sh.sel_digit = d; sh.sel_above = ex; }
   __syncthreads();
   digit = sh.sel_digit;
   above = sh.sel_above;
+}
+
+// One counting round: bins of the participating keys -> warp-private atomics -> CTA histogram.
+template <int E>
+__device__ __forceinline__ void count_round(Shared& sh, int round, const int (&bin)[E], int lane, int wid) {
+  int* wh = sh.whist[wid];
+#pragma unroll
+  for (int i = lane; i < 256; i += 32) wh[i] = 0;
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < E; ++i)
+    if (bin[i] >= 0) atomicAdd(&wh[bin[i]], 1);
+  __syncthreads();
+  if (threadIdx.x < 256) {
+    int s = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) s += sh.whist[w][threadIdx.x];
+    sh.hist[round][threadIdx.x] = s;
+  }
 }
 
 template <typename T, int E, int POOL>
@@ -116,11 +142,10 @@ topk_cluster_kernel(const uint16_t* __restrict__ scores, int n, int kernel_size,
                     const int32_t* __restrict__ k_per_row, int32_t* __restrict__ out_idx, int64_t idx_stride,
                     uint16_t* __restrict__ out_pooled, float* __restrict__ out_sums) {
   constexpr int SL = kThreads * E;          // slice length
-  constexpr int ST = E + 2;                 // staged chunk stride (u16): (E+2)/2 words is odd -> no bank conflicts
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Shared& sh = *reinterpret_cast<Shared*>(smem_raw);
   unsigned char* dyn = smem_raw + ((sizeof(Shared) + 15) & ~15);
-  uint16_t* stage = reinterpret_cast<uint16_t*>(dyn);   // phase 1-2
+  uint16_t* stage = reinterpret_cast<uint16_t*>(dyn);   // phase 1: chunk stride E+2 u16 (odd word stride)
   // phase 3-4 (CTA 0 only, written remotely): keys/indices ping-pong
   uint16_t* skey[2] = {reinterpret_cast<uint16_t*>(dyn), reinterpret_cast<uint16_t*>(dyn) + kMaxK};
   uint32_t* sidx[2] = {reinterpret_cast<uint32_t*>(dyn + 4 * kMaxK), reinterpret_cast<uint32_t*>(dyn + 4 * kMaxK) + kMaxK};
@@ -135,9 +160,19 @@ topk_cluster_kernel(const uint16_t* __restrict__ scores, int n, int kernel_size,
   const int s0 = (int)crank * SL;
 
   // ---- 1. stage [s0-kHalo, s0+SL+kHalo) and pool ------------------------------------------------
-  for (int q = tid; q < SL + 2 * kHalo; q += kThreads) {
-    const int j = s0 - kHalo + q;
-    stage[q + 2 * (q / E)] = (j >= 0 && j < n) ? srow[j] : (uint16_t)0;
+  {
+    // all E+1 loads of a thread are issued before the first store (the row comes from L2 / HBM)
+    uint16_t raw[E + 1];
+#pragma unroll
+    for (int it = 0; it <= E; ++it) {
+      const int q = tid + it * kThreads, j = s0 - kHalo + q;
+      raw[it] = (q < SL + 2 * kHalo && j >= 0 && j < n) ? __ldg(srow + j) : (uint16_t)0;
+    }
+#pragma unroll
+    for (int it = 0; it <= E; ++it) {
+      const int q = tid + it * kThreads;
+      if (q < SL + 2 * kHalo) stage[q + 2 * (q / E)] = raw[it];
+    }
   }
   __syncthreads();
   const int j0 = s0 + tid * E;
@@ -203,33 +238,51 @@ topk_cluster_kernel(const uint16_t* __restrict__ scores, int n, int kernel_size,
     return;
   }
 
-  // ---- 2. radix select, two 8-bit rounds ---------------------------------------------------------
-  int* wh = sh.whist[wid];
-  uint32_t thr_key = 0;
-  int krem = k;
+  // ---- 2a. key range of the row ---------------------------------------------------------------------
+  int kmin = 0xffff, kmax = 0;
 #pragma unroll
-  for (int round = 0; round < 2; ++round) {
-    for (int i = lane; i < 260; i += 32) wh[i] = 0;
-    __syncwarp();
+  for (int i = 0; i < E; ++i)
+    if (i < nvalid) { kmin = min(kmin, (int)keys[i]); kmax = max(kmax, (int)keys[i]); }
+  kmin = __reduce_min_sync(0xffffffffu, kmin);
+  kmax = __reduce_max_sync(0xffffffffu, kmax);
+  if (lane == 0) { sh.warp_tmp[wid] = kmin; sh.warp_tmp2[wid] = kmax; }
+  __syncthreads();
+  if (wid == 0) {
+    const int a = __reduce_min_sync(0xffffffffu, sh.warp_tmp[lane]);
+    const int b2 = __reduce_max_sync(0xffffffffu, sh.warp_tmp2[lane]);
+    if (lane == 0) { sh.mm[0] = a; sh.mm[1] = b2; }
+  }
+  cluster_sync();
+  kmin = 0xffff; kmax = 0;
+  for (uint32_t c = 0; c < csize; ++c) {
+    kmin = min(kmin, (int)ld_cluster_u32(map_to_rank(&sh.mm[0], c)));
+    kmax = max(kmax, (int)ld_cluster_u32(map_to_rank(&sh.mm[1], c)));
+  }
+  const int range = kmax - kmin;
+  const int sh1 = range < 256 ? 0 : (32 - __clz(range)) - 8;  // bins of 2^sh1 keys, <= 256 bins
+
+  // ---- 2b. counting rounds -----------------------------------------------------------------------------
+  int krem = k, thr_key;
+  {
+    int bin[E];
 #pragma unroll
-    for (int i = 0; i < E; ++i) {
-      const bool in = i < nvalid && (round == 0 || (keys[i] >> 8) == thr_key);
-      const int dgt = in ? (int)((round == 0 ? keys[i] >> 8 : keys[i]) & 255u) : 256 + (lane & 3);
-      warp_count_digit(wh, dgt, lane);
-      __syncwarp();
-    }
-    __syncthreads();
-    {
-      int s = 0;
-#pragma unroll
-      for (int w = 0; w < kWarps; ++w) s += sh.whist[w][tid];
-      sh.hist[round][tid] = s;
-    }
-    cluster_sync();  // every CTA's hist[round] is complete and visible
-    int digit, above;
-    cluster_threshold(sh, round, krem, csize, digit, above);
-    thr_key = (thr_key << 8) | (uint32_t)digit;
+    for (int i = 0; i < E; ++i) bin[i] = i < nvalid ? ((int)keys[i] - kmin) >> sh1 : -1;
+    count_round<E>(sh, 0, bin, lane, wid);
+    cluster_sync();  // every CTA's hist[0] is complete and visible
+    int b1, above;
+    cluster_threshold(sh, 0, krem, csize, b1, above);
     krem -= above;
+    thr_key = kmin + (b1 << sh1);
+    if (sh1 > 0) {
+#pragma unroll
+      for (int i = 0; i < E; ++i) bin[i] = (bin[i] == b1) ? ((int)keys[i] - thr_key) : -1;
+      count_round<E>(sh, 1, bin, lane, wid);
+      cluster_sync();
+      int b2v, above2;
+      cluster_threshold(sh, 1, krem, csize, b2v, above2);
+      krem -= above2;
+      thr_key += b2v;
+    }
   }
   const int need_eq = krem, count_gt = k - krem;
 
@@ -237,8 +290,8 @@ topk_cluster_kernel(const uint16_t* __restrict__ scores, int n, int kernel_size,
   int gt = 0, eq = 0;
 #pragma unroll
   for (int i = 0; i < E; ++i) {
-    gt += (i < nvalid && keys[i] > thr_key);
-    eq += (i < nvalid && keys[i] == thr_key);
+    gt += (i < nvalid && (int)keys[i] > thr_key);
+    eq += (i < nvalid && (int)keys[i] == thr_key);
   }
   int total;
   const int ex = block_scan_excl(gt | (eq << 16), sh.warp_tmp, total);
@@ -256,8 +309,8 @@ topk_cluster_kernel(const uint16_t* __restrict__ scores, int n, int kernel_size,
   for (int i = 0; i < E; ++i) {
     if (i < nvalid) {
       int pos = -1;
-      if (keys[i] > thr_key) pos = gpos++;
-      else if (keys[i] == thr_key) { if (epos < need_eq) pos = count_gt + epos; ++epos; }
+      if ((int)keys[i] > thr_key) pos = gpos++;
+      else if ((int)keys[i] == thr_key) { if (epos < need_eq) pos = count_gt + epos; ++epos; }
       if (pos >= 0) {
         st_cluster_u16(rkey + 2u * pos, (uint16_t)keys[i]);
         st_cluster_u32(ridx + 4u * pos, (uint32_t)(j0 + i));
@@ -282,42 +335,44 @@ topk_cluster_kernel(const uint16_t* __restrict__ scores, int n, int kernel_size,
       out_sums[2 * row] = a;
       out_sums[2 * row + 1] = bsum;
     }
-    const int V = (k + kThreads - 1) / kThreads;          // slots per thread
+    int* wh = sh.whist[wid];
+    const int V = (k + kThreads - 1) / kThreads;          // slots per thread (<= 8)
     const int per_warp = V * 32;                          // warp w owns elements [w*per_warp, (w+1)*per_warp)
     int cur = 0;
     for (int pass = 0; pass < 2; ++pass) {
-      for (int i = lane; i < 260; i += 32) wh[i] = 0;
-      __syncthreads();
-      // count + stable rank inside this warp's run (kept in registers via re-computation below)
-      // pass A: per-warp digit totals
+#pragma unroll
+      for (int i = lane; i < 256; i += 32) wh[i] = 0;
+      __syncwarp();
+      // per-warp digit totals (elements of a warp's run are visited in order, so ranks are stable)
       for (int v = 0; v < V; ++v) {
         const int o = wid * per_warp + v * 32 + lane;
-        const int dgt = o < k ? 255 - (int)((skey[cur][o] >> (8 * pass)) & 255u) : 256 + (lane & 3);
-        warp_count_digit(wh, dgt, lane);
-        __syncwarp();
+        if (o < k) atomicAdd(&wh[255 - (int)((skey[cur][o] >> (8 * pass)) & 255u)], 1);
       }
       __syncthreads();
-      // digit bases: thread t <-> digit t; exclusive scan over digits of the per-digit totals
-      int wcount[kWarps];
+      // digit bases: thread t < 256 <-> digit t; exclusive scan over digits of the per-digit totals,
+      // then the per-warp counters become start offsets: whist[w][d] = base[d] + sum_{w'<w} count[w'][d]
       int tot = 0;
+      if (tid < 256) {
 #pragma unroll
-      for (int w = 0; w < kWarps; ++w) { wcount[w] = sh.whist[w][tid]; tot += wcount[w]; }
+        for (int w = 0; w < kWarps; ++w) tot += sh.whist[w][tid];
+      }
       int total2;
       int dbase = block_scan_excl(tot, sh.warp_tmp, total2);
-      // turn the per-warp counters into start offsets: whist[w][d] = dbase[d] + sum_{w'<w} count[w'][d]
+      if (tid < 256) {
 #pragma unroll
-      for (int w = 0; w < kWarps; ++w) { sh.whist[w][tid] = dbase; dbase += wcount[w]; }
+        for (int w = 0; w < kWarps; ++w) { const int c = sh.whist[w][tid]; sh.whist[w][tid] = dbase; dbase += c; }
+      }
       __syncthreads();
-      // pass B: scatter in the same (warp, slot, lane) order
+      // scatter in (warp, slot, lane) order with stable in-warp ranks
       for (int v = 0; v < V; ++v) {
         const int o = wid * per_warp + v * 32 + lane;
         const bool in = o < k;
         const uint16_t key = in ? skey[cur][o] : (uint16_t)0;
         const uint32_t idx = in ? sidx[cur][o] : 0u;
-        const int dgt = in ? 255 - (int)((key >> (8 * pass)) & 255u) : 256 + (lane & 3);
-        const int dst = warp_count_digit(wh, dgt, lane);
+        // lanes past the end use digit 255 of the LAST pass ordering: they come after every real element
+        const int dgt = in ? 255 - (int)((key >> (8 * pass)) & 255u) : 255;
+        const int dst = warp_rank_digit(wh, dgt, lane);
         if (in) { skey[cur ^ 1][dst] = key; sidx[cur ^ 1][dst] = idx; }
-        __syncwarp();
       }
       __syncthreads();
       cur ^= 1;
@@ -357,13 +412,11 @@ static int launch(const void* scores, int rows, int n, int C, int kernel_size, i
 template <typename T, int POOL>
 static int dispatch_e(const void* scores, int rows, int n, int kernel_size, int k, const int32_t* k_per_row,
                       int32_t* out_idx, int64_t idx_stride, void* out_pooled, float* out_sums, cudaStream_t stream) {
-  // slice = 256*E elements per CTA; small rows use one CTA, long rows up to 16 CTAs of 8192
-  if (n <= 1024) return launch<T, 4, POOL>(scores, rows, n, 1, kernel_size, k, k_per_row, out_idx, idx_stride, out_pooled, out_sums, stream);
-  if (n <= 4096) return launch<T, 8, POOL>(scores, rows, n, (n + 2047) / 2048, kernel_size, k, k_per_row, out_idx, idx_stride, out_pooled, out_sums, stream);
-  if (n <= 16384) return launch<T, 16, POOL>(scores, rows, n, n <= 8192 ? 2 : 4, kernel_size, k, k_per_row, out_idx, idx_stride, out_pooled, out_sums, stream);
-  int C = 4;
-  while (C * 8192 < n) C <<= 1;
-  return launch<T, 32, POOL>(scores, rows, n, C, kernel_size, k, k_per_row, out_idx, idx_stride, out_pooled, out_sums, stream);
+  // slice = 1024*E scores per CTA
+  if (n <= 4096) return launch<T, 4, POOL>(scores, rows, n, 1, kernel_size, k, k_per_row, out_idx, idx_stride, out_pooled, out_sums, stream);
+  if (n <= 16384) return launch<T, 4, POOL>(scores, rows, n, (n + 4095) / 4096, kernel_size, k, k_per_row, out_idx, idx_stride, out_pooled, out_sums, stream);
+  if (n <= 65536) return launch<T, 8, POOL>(scores, rows, n, (n + 8191) / 8192, kernel_size, k, k_per_row, out_idx, idx_stride, out_pooled, out_sums, stream);
+  return launch<T, 16, POOL>(scores, rows, n, (n + 16383) / 16384, kernel_size, k, k_per_row, out_idx, idx_stride, out_pooled, out_sums, stream);
 }
 
 template <typename T>
@@ -380,7 +433,7 @@ static int dispatch_pool(int pool, const void* scores, int rows, int n, int kern
 int pool_topk_cluster(const void* scores, int rows, int n, int dtype, int kernel_size, int pool, int k,
                       const int32_t* k_per_row, int32_t* out_idx, int64_t idx_stride, void* out_pooled, float* out_sums,
                       cudaStream_t stream) {
-  if (k > cl::kMaxK || n > 16 * 8192 || (pool != KVC_POOL_NONE && kernel_size > 2 * cl::kHalo + 1) || rows > 65535)
+  if (k > cl::kMaxK || n > 8 * 16384 || (pool != KVC_POOL_NONE && kernel_size > 2 * cl::kHalo + 1) || rows > 65535)
     return 1;
   return dtype == KVC_BF16
              ? cl::dispatch_pool<Bf16>(pool, scores, rows, n, kernel_size, k, k_per_row, out_idx, idx_stride, out_pooled, out_sums, stream)

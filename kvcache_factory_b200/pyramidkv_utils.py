@@ -26,6 +26,29 @@ from . import _native as N
 
 _VERBOSE = os.environ.get("KVC_VERBOSE", "0") == "1"
 
+# ---- asynchronous tail ---------------------------------------------------------------------------
+# The compressed cache of a prefill is first read at the next decode step, so only the scoring has to
+# sit on the caller's stream: with ``async_tail`` the select + gather kernels of layer l run on a
+# per-device side stream and overlap whatever the caller enqueues next (the next layer's QKV /
+# attention, or the next layer's scoring).  ``wait_for_compression`` joins the side stream back.
+_side_streams = {}
+
+
+def compression_stream(device) -> "torch.cuda.Stream":
+    device = torch.device(device)
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device)
+    return _side_streams[key]
+
+
+def wait_for_compression(device=None) -> None:
+    """Make the current stream wait for every asynchronous select/gather issued so far."""
+    keys = list(_side_streams) if device is None else [torch.device(device).index or 0]
+    for key in keys:
+        if key in _side_streams:
+            torch.cuda.current_stream(key).wait_stream(_side_streams[key])
+
 
 def _trace(msg: str) -> None:
     if _VERBOSE:
@@ -85,6 +108,7 @@ class _ScoredCluster:
     merge = None
     keep_debug = False          # tests set this to read back scores / indices
     score_impl = N.IMPL_AUTO    # tests/bench may pin KVC_IMPL_MMA_SYNC or KVC_IMPL_TCGEN05
+    async_tail = False          # run select + gather on the side stream (see wait_for_compression)
 
     def _configure(self, window_size, max_capacity_prompt, kernel_size, pooling, merge):
         self.window_size = window_size
@@ -131,6 +155,20 @@ class _ScoredCluster:
             scores = N.h2o_scores(query_states, key_states, w)
         else:
             scores = None
+        if self.async_tail and scores is not None:
+            dev = key_states.device
+            main, side = torch.cuda.current_stream(dev), compression_stream(dev)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                idx, pooled, _ = N.pool_topk(scores, self.kernel_size, pooling, n_keep, want_pooled=self.keep_debug)
+                out = N.gather_dense(key_states, value_states, idx, Hq, n_keep, w)
+            if not torch.cuda.is_current_stream_capturing():
+                for t in (scores, key_states, value_states):
+                    t.record_stream(side)
+            self._inflight = (scores, idx)
+            if self.keep_debug:
+                self.debug = dict(scores=scores, pooled=pooled, indices=idx, n_keep=n_keep)
+            return out
         if scores is not None:
             idx, pooled, _ = N.pool_topk(scores, self.kernel_size, pooling, n_keep, want_pooled=self.keep_debug)
         else:
