@@ -244,6 +244,40 @@ def test_window_scores_hf_query_layout(impl):
 
 
 # ------------------------------------------------------------------------------------------------
+# H2O (all-query) scores
+# ------------------------------------------------------------------------------------------------
+H2O_CASES = [
+    # B, Hq, Hkv, L, w
+    (1, 4, 2, 384, 32),
+    (2, 4, 1, 1000, 16),     # ragged L, g = 4, window inside the last tile
+    (1, 2, 2, 129, 8),       # one key past a tile boundary
+    (1, 8, 2, 2048, 64),
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("case", H2O_CASES, ids=lambda c: "B%d_Hq%d_Hkv%d_L%d_w%d" % c)
+def test_h2o_scores_match_oracle(dtype, case):
+    B, Hq, Hkv, L, w = case
+    shape = Shape(B, Hq, Hkv, L, 128)
+    Q, K, V = make_qkv(shape, dtype, layer_idx=6, dist="peaked", window=w)
+    ref = O.window_scores(O.repeat_kv(K, Hq // Hkv), Q, w, "sum", all_queries=True)
+    got = _native.h2o_scores(Q.to(dev()), K.to(dev()), w)
+    torch.cuda.synchronize()
+    assert got.shape == ref.shape and got.dtype == dtype
+    bad, worst = score_mismatch(got, ref, dtype, SCORE_ULPS)
+    exact = float((got.cpu() == ref).float().mean())
+    assert bad == 0.0, f"{bad:.2%} of H2O scores off by more than {SCORE_ULPS} ulps (worst {worst:.1f}x)"
+    assert exact >= 0.80, f"only {exact:.2%} of H2O scores bit-identical to the oracle"
+
+
+@pytest.mark.parametrize("name", golden_cases("h2o"))
+def test_h2o_matches_reference_vectors(name):
+    c, z, (Q, K, V) = load_golden(name)
+    _check_dense(H2OKVCluster(**c["knobs"]), c, z, Q, K, V, _native.IMPL_AUTO)
+
+
+# ------------------------------------------------------------------------------------------------
 # whole update_kv against the reference's vectors
 # ------------------------------------------------------------------------------------------------
 def _check_dense(cluster, c, z, Q, K, V, impl):
