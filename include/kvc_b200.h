@@ -152,6 +152,14 @@ int kvc_adakv_allocate(const void* pooled, const float* sums, int H, int n, int 
                        int w, int32_t* out_cap, int32_t* out_head_lens, int32_t* out_cu_klen,
                        void* workspace, size_t workspace_bytes, void* stream);
 
+/* Multi-GPU building block of the same allocation (one KV-head shard per GPU):
+ * out_hist int32[H,65536] = histogram of each local head's ratio-normalised scores over an
+ * order-preserving 16-bit key (key of +0.0 is 0x8000; larger value -> larger key).  The host sums it
+ * over heads, all-reduces it over the ranks (one 256 KiB collective) and derives the global
+ * threshold and the per-head winner counts (kvcache_factory_b200/sharding.py). */
+int kvc_adakv_key_histogram(const void* pooled, const float* sums, int H, int n, int dtype,
+                            int normalize, int32_t* out_hist, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Flattened-cache append — replaces tiny_api_cuda.update_flatten_view
  * csrc/csrc/cuda_api.cu:55-85 (kernel :11-53), called by DynamicCacheSplitHeadFlatten.update

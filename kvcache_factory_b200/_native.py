@@ -45,6 +45,7 @@ _SIGNATURES = {
                                   _p, _p]),
     "kvc_adakv_allocate_workspace_bytes": (c_size_t, [_i] * 2),
     "kvc_adakv_allocate": (c_int, [_p, _p, _i, _i, _i, _i, c_float, _i, _i, _i, _p, _p, _p, _p, c_size_t, _p]),
+    "kvc_adakv_key_histogram": (c_int, [_p, _p, _i, _i, _i, _i, _p, _p]),
     "kvc_update_flatten_view": (c_int, [_p, _p, _p, _p, _p, _i, _i, _i, _i64, _p]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
@@ -269,6 +270,18 @@ def adakv_allocate(pooled: torch.Tensor, sums: torch.Tensor, base_capacity: int,
             int(base_capacity * floor_ratio), int(bool(normalize)), window_size,
             cap.data_ptr(), head_lens.data_ptr(), cu_klen.data_ptr(), ws.data_ptr(), ws.numel(), _stream(dev)))
     return cap, head_lens, cu_klen
+
+
+def adakv_key_histogram(pooled: torch.Tensor, sums: torch.Tensor, normalize: bool) -> torch.Tensor:
+    """int32 [H,65536] histogram of each head's ratio-normalised scores over the ordered 16-bit key."""
+    dev = _require_cuda(pooled, sums)
+    H, n = pooled.shape
+    hist = torch.empty((H, 65536), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _check("kvc_adakv_key_histogram", lib().kvc_adakv_key_histogram(
+            pooled.contiguous().data_ptr(), sums.data_ptr(), H, n, dtype_code(pooled.dtype), int(bool(normalize)),
+            hist.data_ptr(), _stream(dev)))
+    return hist
 
 
 def update_flatten_view(cache: torch.Tensor, state: torch.Tensor, headlens: torch.Tensor,

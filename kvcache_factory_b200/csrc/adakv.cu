@@ -207,3 +207,43 @@ int adakv_allocate(const void* pooled, const float* sums, int H, int n, int dtyp
 }
 
 }  // namespace kvc
+
+// ---- multi-GPU building block ------------------------------------------------------------------
+// Full-resolution (65536-bin) histogram of each local head's ratio-normalised 16-bit keys.  Summed
+// over heads and all-reduced over the ranks of a head-sharded layout it yields the exact global
+// top-(H*base) threshold with ONE collective (256 KiB); see kvcache_factory_b200/sharding.py.
+namespace kvc {
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+ada_key_histogram_kernel(const uint16_t* __restrict__ pooled, const float* __restrict__ sums, int n, int normalize,
+                         int* __restrict__ hist) {
+  const int h = blockIdx.y;
+  float ratio = 1.f;
+  if (normalize) {
+    const float top = T::to_float(T::round1(sums[2 * h])), all = T::to_float(T::round1(sums[2 * h + 1]));
+    ratio = T::to_float(T::round1(top / all));
+  }
+  const uint16_t* row = pooled + (int64_t)h * n;
+  int* hh = hist + (int64_t)h * 65536;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    uint32_t bits = row[j];
+    if (normalize) bits = T::round1(T::to_float((uint16_t)bits) * ratio);
+    atomicAdd(&hh[float16_bits_to_key(bits)], 1);
+  }
+}
+
+int adakv_key_histogram(const void* pooled, const float* sums, int H, int n, int dtype, int normalize, int32_t* out_hist,
+                        cudaStream_t stream) {
+  KVC_CUDA_TRY(cudaMemsetAsync(out_hist, 0, (size_t)H * 65536 * sizeof(int32_t), stream));
+  int gx = (n + 256 * 8 - 1) / (256 * 8);
+  if (gx < 1) gx = 1;
+  dim3 grid(gx, H);
+  if (dtype == KVC_BF16)
+    ada_key_histogram_kernel<Bf16><<<grid, 256, 0, stream>>>((const uint16_t*)pooled, sums, n, normalize, out_hist);
+  else
+    ada_key_histogram_kernel<Fp16><<<grid, 256, 0, stream>>>((const uint16_t*)pooled, sums, n, normalize, out_hist);
+  return launch_status("ada_key_histogram_kernel");
+}
+
+}  // namespace kvc

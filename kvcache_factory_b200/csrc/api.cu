@@ -27,6 +27,7 @@ size_t h2o_scores_workspace_bytes(int B, int Hq, int Hkv, int L, int d, int w);
 int h2o_scores(const void*, int64_t, int64_t, int64_t, const void*, int64_t, int64_t, int64_t, int, int, int, int,
                int, int, int, void*, void*, size_t, cudaStream_t);
 size_t adakv_allocate_workspace_bytes(int H, int n);
+int adakv_key_histogram(const void*, const float*, int, int, int, int, int32_t*, cudaStream_t);
 int adakv_allocate(const void*, const float*, int, int, int, int, float, int, int, int, int32_t*, int32_t*, int32_t*,
                    void*, size_t, cudaStream_t);
 
@@ -203,6 +204,15 @@ int kvc_adakv_allocate(const void* pooled, const float* sums, int H, int n, int 
   KVC_REQUIRE(dtype == KVC_BF16 || dtype == KVC_FP16, KVC_ERR_UNSUPPORTED, "dtype %d", dtype);
   return adakv_allocate(pooled, sums, H, n, dtype, base_capacity, one_minus_floor, floor_capacity, normalize, w,
                         out_cap, out_head_lens, out_cu_klen, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int kvc_adakv_key_histogram(const void* pooled, const float* sums, int H, int n, int dtype, int normalize,
+                            int32_t* out_hist, void* stream) {
+  if (int rc = check_device()) return rc;
+  KVC_REQUIRE(pooled && out_hist && (sums || !normalize), KVC_ERR_ARG, "null pointer");
+  KVC_REQUIRE(H > 0 && n > 0, KVC_ERR_ARG, "H=%d n=%d", H, n);
+  KVC_REQUIRE(dtype == KVC_BF16 || dtype == KVC_FP16, KVC_ERR_UNSUPPORTED, "dtype %d", dtype);
+  return adakv_key_histogram(pooled, sums, H, n, dtype, normalize, out_hist, (cudaStream_t)stream);
 }
 
 int kvc_update_flatten_view(void* dst, const void* src, const void* state, const int32_t* headlens,
