@@ -1,0 +1,541 @@
+// Window scoring, single-launch version of scores_tc.cu: both softmax passes in ONE persistent kernel
+// with a grid-wide barrier in between.
+//
+//   every CTA:  pass 1 over its chunk of keys (stats)  ->  publish (m, Z) partials  ->  grid barrier
+//               ->  fold all chunks' partials into c_row  ->  pass 2 over the same chunk (scores)
+//
+// Only the 8 epilogue warps wait at the barrier.  The TMA producer and the MMA issuer run straight
+// on into pass 2 (K tiles and Q.K^T do not depend on the statistics), so when the barrier opens the
+// 4 TMEM accumulator buffers already hold pass-2 tiles and the K ring is full: the barrier costs the
+// skew between CTAs, not a pipeline refill.  Pass 2 walks the chunk backwards, i.e. starts with the
+// tiles that were read last (still in L2).  Versus two launches this saves a kernel launch + ramp,
+// one Q staging / TMEM allocation / stats re-read, and the drain between the kernels.
+//
+// Requires all CTAs to be co-resident (grid <= #SMs, one CTA per SM: the grid is sized that way).
+// Math, rounding points and operand roles are identical to scores_tc.cu.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace kvc {
+namespace tcf {
+
+constexpr int kTile = 128;
+constexpr int kD = 128;
+constexpr int kHalfBytes = kTile * 64 * 2;
+constexpr int kTileBytes = 2 * kHalfBytes;
+constexpr int kNumBuf = 4;
+constexpr int kEpiWarps = 8;
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kThreads = 32 * (2 + kEpiWarps);
+
+struct Params {
+  const uint16_t* q; int64_t q_sb, q_sh, q_sl;
+  int B, Hq, Hkv, L, w, groups;
+  int chunk_tiles, nchunks;
+  float scale;
+  int reduce_mean;
+  float2* stats;        // [units][nchunks][RB*128]
+  uint16_t* out;        // [B,Hq,L-w]
+  unsigned* sync_count; // grid barrier counter, zeroed before the launch
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!done && spin > (1u << 22)) {
+      printf("kvc scores_fused: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tmap, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,"
+      "%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3fffu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ uint32_t instr_desc(int fmt, int M, int N) {
+  return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+template <int RB>
+struct Smem {
+  static constexpr int kStages = RB == 1 ? 5 : 4;
+  static constexpr int kQBytes = RB * kTileBytes;
+  static constexpr int kKBytes = kStages * kTileBytes;
+  static constexpr int kBarOff = kQBytes + kKBytes;
+  static constexpr int kNumBars = 2 * kStages + 2 * kNumBuf + 1;
+  static constexpr int kTmemPtrOff = kBarOff + kNumBars * 8;
+  static constexpr int kCrowOff = (kTmemPtrOff + 4 + 15) & ~15;        // float[RB*128]
+  static constexpr int kXstatOff = kCrowOff + RB * 128 * 4;            // float2[RB][2][128]
+  static constexpr int kTotal = kXstatOff + RB * 2 * 128 * 8;
+  static constexpr int kAlloc = kTotal + 1024;
+};
+
+// TMEM accumulator (4 x 32 columns) -> registers, hand the buffer back, apply the reference's two
+// roundings (GEMM result -> dtype, * 1/sqrt(d) in fp32 -> dtype): 64 packed pairs.
+template <typename T>
+__device__ __forceinline__ void load_round(uint32_t taddr, float scale, uint32_t (&r2)[64], uint32_t tempty_bar, int lane) {
+  uint32_t v[4][32];
+#pragma unroll
+  for (int cc = 0; cc < 4; ++cc) tmem_ld32(taddr + cc * 32, v[cc]);
+  tmem_ld_wait();
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(tempty_bar);
+  const float2 scale2 = make_float2(scale, scale);
+#pragma unroll
+  for (int cc = 0; cc < 4; ++cc) {
+    uint32_t p1[16];
+    float2 f[16];
+#pragma unroll
+    for (int pi = 0; pi < 16; ++pi) p1[pi] = T::pack(__uint_as_float(v[cc][2 * pi]), __uint_as_float(v[cc][2 * pi + 1]));
+#pragma unroll
+    for (int pi = 0; pi < 16; ++pi) f[pi] = __fmul2_rn(make_float2(T::lo(p1[pi]), T::hi(p1[pi])), scale2);
+#pragma unroll
+    for (int pi = 0; pi < 16; ++pi) r2[cc * 16 + pi] = T::pack(f[pi].x, f[pi].y);
+  }
+}
+
+template <typename T, int RB, int W>
+__global__ void __launch_bounds__(kThreads, 1)
+window_score_fused_kernel(const __grid_constant__ CUtensorMap tmap_k, const Params p) {
+  using SM = Smem<RB>;
+  constexpr int S = SM::kStages;
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  unsigned char* smem = smem_raw + (base - raw_addr);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int chunk = blockIdx.x, unit = blockIdx.y;
+  const int b = unit / p.Hkv, kvh = unit % p.Hkv;
+  const int nscore = p.L - p.w;
+  const int tile_begin = chunk * p.chunk_tiles;
+  const int n1 = max(0, min(tile_begin + p.chunk_tiles, (p.L + kTile - 1) / kTile) - tile_begin);    // pass-1 tiles
+  const int n2 = max(0, min(tile_begin + p.chunk_tiles, (nscore + kTile - 1) / kTile) - tile_begin); // pass-2 tiles
+  const int nq = RB == 1 ? p.groups * p.w : 128;
+  // item it < n1: pass-1 tile tile_begin+it; item it >= n1: pass-2 tile, walking the chunk backwards
+  auto tile_of = [&](int it) { return it < n1 ? tile_begin + it : tile_begin + (n2 - 1 - (it - n1)); };
+
+  const uint32_t q_s = base, k_s = base + SM::kQBytes, bar_s = base + SM::kBarOff;
+  auto kfull = [&](int s) { return bar_s + 8u * s; };
+  auto kempty = [&](int s) { return bar_s + 8u * (S + s); };
+  auto tfull = [&](int i) { return bar_s + 8u * (2 * S + i); };
+  auto tempty = [&](int i) { return bar_s + 8u * (2 * S + kNumBuf + i); };
+  const uint32_t qbar = bar_s + 8u * (2 * S + 2 * kNumBuf);
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + SM::kTmemPtrOff);
+  float* crow = reinterpret_cast<float*>(smem + SM::kCrowOff);
+  float2* xstat = reinterpret_cast<float2*>(smem + SM::kXstatOff);
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(kfull(s), 1); mbar_init(kempty(s), 1); }
+    for (int i = 0; i < kNumBuf; ++i) { mbar_init(tfull(i), 1); mbar_init(tempty(i), 4); }
+    mbar_init(qbar, kEpiThreads);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===== TMA producer: one stream of n1 + n2 tiles =====
+    if (lane == 0) {
+      for (int it = 0; it < n1 + n2; ++it) {
+        const int s = it % S;
+        mbar_wait(kempty(s), ((it / S) & 1) ^ 1);
+        mbar_expect_tx(kfull(s), kTileBytes);
+        const int key0 = tile_of(it) * kTile;
+        tma_load_4d(k_s + s * kTileBytes, &tmap_k, kfull(s), 0, key0, kvh, b);
+        tma_load_4d(k_s + s * kTileBytes + kHalfBytes, &tmap_k, kfull(s), 64, key0, kvh, b);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: pass 1 D = Q.K^T (lanes = query rows), pass 2 D = K.Q^T (lanes = keys) =====
+    if (lane == 0) {
+      const int fmt = T::kDtype == KVC_BF16 ? 1 : 0;
+      const uint32_t idesc1 = instr_desc(fmt, 128, 128), idesc2 = instr_desc(fmt, 128, nq);
+      mbar_wait(qbar, 0);
+      tc_fence_after();
+      for (int it = 0; it < n1 + n2; ++it) {
+        const int s = it % S;
+        const bool second = it >= n1;
+        mbar_wait(kfull(s), (it / S) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int rb = 0; rb < RB; ++rb) {
+          const int j = it * RB + rb, buf = j % kNumBuf;
+          mbar_wait(tempty(buf), ((j / kNumBuf) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t ks = k_s + s * kTileBytes, qs = q_s + rb * kTileBytes;
+#pragma unroll
+          for (int k = 0; k < kD / 16; ++k) {
+            const uint32_t off = (k >> 2) * kHalfBytes + (k & 3) * 32;
+            const uint64_t kd = smem_desc(ks + off), qd = smem_desc(qs + off);
+            tc_mma(tmem_base + buf * 128, second ? kd : qd, second ? qd : kd, second ? idesc2 : idesc1, k > 0);
+          }
+          tc_commit(tfull(buf));
+        }
+        tc_commit(kempty(s));
+      }
+    }
+  } else {
+    // ===== epilogue warps =====
+    const int et = tid - 64;
+    const int wg = (warp - 2) >> 2;
+    const int quad = warp & 3;
+    const int r_loc = quad * 32 + lane;
+    const float2 l2e2 = make_float2(kLog2e, kLog2e);
+
+    // stage the Q block(s): canonical K-major SWIZZLE_128B layout, all chunks in flight
+#pragma unroll
+    for (int it = 0; it < RB * 128 * 16 / kEpiThreads; ++it) {
+      const int e = et + it * kEpiThreads;
+      const int rg = e >> 4, c16 = e & 15;
+      const int rb = rg >> 7, r = rg & 127;
+      const int hl = rg / W, i = rg % W;
+      const bool ok = hl < p.groups;
+      const uint16_t* src = p.q + b * p.q_sb + (int64_t)(kvh * p.groups + (ok ? hl : 0)) * p.q_sh +
+                            (int64_t)(nscore + i) * p.q_sl + c16 * 8;
+      const uint32_t dst = q_s + rb * kTileBytes + (c16 >> 3) * kHalfBytes + r * 128 + (((c16 & 7) ^ (r & 7)) << 4);
+      const int sz = ok ? 16 : 0;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_arrive(qbar);
+
+    // ---------------- pass 1: thread <-> query row, columns are keys ----------------
+    float m_run[RB], z_run[RB];
+#pragma unroll
+    for (int rb = 0; rb < RB; ++rb) { m_run[rb] = -1e30f; z_run[rb] = 0.f; }
+    int j = wg;
+    for (; j < n1 * RB; j += 2) {
+      const int it = j / RB, rb = j % RB, buf = j % kNumBuf;
+      const int key0 = tile_of(it) * kTile;
+      mbar_wait(tfull(buf), (j / kNumBuf) & 1);
+      tc_fence_after();
+      uint32_t r2[64];
+      load_round<T>(tmem_base + ((uint32_t)(quad * 32) << 16) + buf * 128, p.scale, r2, tempty(buf), lane);
+      if (key0 + kTile > nscore) {  // tile touches the w x w causal block or the ragged end
+        const int rg = rb * 128 + r_loc;
+        const int hl = rg / W, wi = rg % W;
+        const int last_key = min(p.L - 1, hl < p.groups ? nscore + wi : p.L - 1);
+#pragma unroll
+        for (int i = 0; i < 64; ++i) {
+          const int key = key0 + 2 * i;
+          if (key > last_key) r2[i] = (r2[i] & 0xffff0000u) | (T::kNegInfPair & 0xffffu);
+          if (key + 1 > last_key) r2[i] = (r2[i] & 0x0000ffffu) | (T::kNegInfPair & 0xffff0000u);
+        }
+      }
+      uint32_t pm = r2[0];
+#pragma unroll
+      for (int i = 1; i < 64; ++i) pm = T::max2(pm, r2[i]);
+      const float m_new = fmaxf(m_run[rb], fmaxf(T::lo(pm), T::hi(pm)));
+      const float2 ml2 = make_float2(-m_new * kLog2e, -m_new * kLog2e);
+      float2 zacc[4];
+      zacc[0] = make_float2(z_run[rb] * fast_exp2((m_run[rb] - m_new) * kLog2e), 0.f);
+      zacc[1] = zacc[2] = zacc[3] = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int bt = 0; bt < 4; ++bt) {
+        float2 a[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) a[i] = __ffma2_rn(make_float2(T::lo(r2[bt * 16 + i]), T::hi(r2[bt * 16 + i])), l2e2, ml2);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) a[i] = make_float2(fast_exp2(a[i].x), fast_exp2(a[i].y));
+#pragma unroll
+        for (int i = 0; i < 16; ++i) zacc[i & 3] = __fadd2_rn(zacc[i & 3], a[i]);
+      }
+      const float2 z2 = __fadd2_rn(__fadd2_rn(zacc[0], zacc[1]), __fadd2_rn(zacc[2], zacc[3]));
+      m_run[rb] = m_new;
+      z_run[rb] = z2.x + z2.y;
+    }
+
+    // ---------------- publish partials, grid barrier, fold all chunks into c_row ----------------
+#pragma unroll
+    for (int rb = 0; rb < RB; ++rb) xstat[(rb * 2 + wg) * 128 + r_loc] = make_float2(m_run[rb], z_run[rb]);
+    epi_sync();
+    for (int r = et; r < RB * 128; r += kEpiThreads) {
+      const int rb = r >> 7, rl = r & 127;
+      const float2 a = xstat[(rb * 2 + 0) * 128 + rl], c = xstat[(rb * 2 + 1) * 128 + rl];
+      const float mn = fmaxf(a.x, c.x);
+      const float z = a.y * fast_exp2((a.x - mn) * kLog2e) + c.y * fast_exp2((c.x - mn) * kLog2e);
+      p.stats[((int64_t)unit * p.nchunks + chunk) * (RB * 128) + r] = make_float2(mn, z);
+    }
+    __threadfence();
+    epi_sync();
+    if (et == 0) {
+      const unsigned total = gridDim.x * gridDim.y;
+      atomicAdd(p.sync_count, 1u);
+      unsigned seen = 0;
+      for (unsigned spin = 0; seen < total; ++spin) {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.sync_count) : "memory");
+        if (seen < total) {
+          __nanosleep(64);
+          if (spin > (1u << 24)) {
+            printf("kvc scores_fused: grid barrier timed out (block %d,%d: %u of %u arrived)\n", blockIdx.x, blockIdx.y, seen, total);
+            __trap();
+          }
+        }
+      }
+    }
+    epi_sync();
+    for (int r = et; r < RB * 128; r += kEpiThreads) {
+      const float2* st = p.stats + (int64_t)unit * p.nchunks * (RB * 128) + r;
+      float M = -1e30f, Z = 0.f;
+      for (int c0 = 0; c0 < p.nchunks; c0 += 8) {
+        float2 sv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          sv[u] = make_float2(-1e30f, 0.f);
+          if (c0 + u < p.nchunks) {
+            const float2* a = st + (int64_t)(c0 + u) * (RB * 128);
+            asm volatile("ld.global.cg.v2.f32 {%0, %1}, [%2];" : "=f"(sv[u].x), "=f"(sv[u].y) : "l"(a) : "memory");  // written by other SMs: bypass L1
+          }
+        }
+        float mx = M;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) mx = fmaxf(mx, sv[u].x);
+        Z *= fast_exp2((M - mx) * kLog2e);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) Z += sv[u].y * fast_exp2((sv[u].x - mx) * kLog2e);
+        M = mx;
+      }
+      crow[r] = (r / W < p.groups) ? (-M * kLog2e - log2f(Z)) : -INFINITY;
+    }
+    epi_sync();
+
+    // ---------------- pass 2: thread <-> key, columns are the stacked query rows ----------------
+    constexpr int kHeadsPerBlk = 128 / W;
+    for (; j < (n1 + n2) * RB; j += 2) {
+      const int it = j / RB, rb = j % RB, buf = j % kNumBuf;
+      const int key0 = tile_of(it) * kTile;
+      mbar_wait(tfull(buf), (j / kNumBuf) & 1);
+      tc_fence_after();
+      uint32_t r2[64];
+      load_round<T>(tmem_base + ((uint32_t)(quad * 32) << 16) + buf * 128, p.scale, r2, tempty(buf), lane);
+      float2 acc[kHeadsPerBlk];
+#pragma unroll
+      for (int h = 0; h < kHeadsPerBlk; ++h) acc[h] = make_float2(0.f, 0.f);
+      const float* cr = crow + rb * 128;
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        float2 a[16];
+#pragma unroll
+        for (int q4 = 0; q4 < 8; ++q4) {
+          const float4 c4 = *reinterpret_cast<const float4*>(cr + cc * 32 + q4 * 4);
+          a[2 * q4] = __ffma2_rn(make_float2(T::lo(r2[cc * 16 + 2 * q4]), T::hi(r2[cc * 16 + 2 * q4])), l2e2,
+                                 make_float2(c4.x, c4.y));
+          a[2 * q4 + 1] = __ffma2_rn(make_float2(T::lo(r2[cc * 16 + 2 * q4 + 1]), T::hi(r2[cc * 16 + 2 * q4 + 1])), l2e2,
+                                     make_float2(c4.z, c4.w));
+        }
+        uint32_t pp[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pp[i] = T::pack(fast_exp2(a[i].x), fast_exp2(a[i].y));
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int col = cc * 32 + 2 * i;
+          acc[col / W] = __fadd2_rn(acc[col / W], make_float2(T::lo(pp[i]), T::hi(pp[i])));
+        }
+      }
+      const int key = key0 + r_loc;
+      if (key < nscore) {
+#pragma unroll
+        for (int h = 0; h < kHeadsPerBlk; ++h) {
+          const int head = rb * kHeadsPerBlk + h;
+          if (head < p.groups) {
+            float s = acc[h].x + acc[h].y;
+            if (p.reduce_mean) s = s / (float)p.w;
+            p.out[((int64_t)b * p.Hq + kvh * p.groups + head) * nscore + key] = T::round1(s);
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+struct Plan {
+  int rb, chunk_tiles, nchunks;
+  size_t stats_bytes;
+};
+
+static Plan make_plan(int B, int Hq, int Hkv, int L, int w) {
+  Plan pl{};
+  const int g = Hq / Hkv;
+  pl.rb = (g * w + 127) / 128;
+  const int units = B * Hkv;
+  const int tiles = (L + kTile - 1) / kTile;
+  int cu = sm_count() / units;
+  if (cu < 1) cu = 1;
+  pl.chunk_tiles = (tiles + cu - 1) / cu;
+  pl.nchunks = (tiles + pl.chunk_tiles - 1) / pl.chunk_tiles;
+  pl.stats_bytes = ((size_t)units * pl.nchunks * pl.rb * 128 * sizeof(float2) + 255) & ~(size_t)255;
+  return pl;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)ptr;
+  }
+  return fn;
+}
+
+template <typename T, int RB, int W>
+static int launch(const CUtensorMap& tmap, const Params& sp, int units, cudaStream_t stream) {
+  auto kern = window_score_fused_kernel<T, RB, W>;
+  const int smem = Smem<RB>::kAlloc;
+  KVC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  KVC_CUDA_TRY(cudaMemsetAsync(sp.sync_count, 0, sizeof(unsigned), stream));
+  // cooperative launch: the grid is scheduled only when every CTA can be resident, so two grids
+  // with barriers (other streams / processes) can never hold each other's SMs hostage
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(sp.nchunks, units);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  KVC_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, tmap, sp));
+  return launch_status("window_score_fused_kernel");
+}
+
+template <typename T, int RB>
+static int dispatch_w(const CUtensorMap& tmap, const Params& sp, int units, cudaStream_t stream) {
+  switch (sp.w) {
+    case 8: return launch<T, RB, 8>(tmap, sp, units, stream);
+    case 16: return launch<T, RB, 16>(tmap, sp, units, stream);
+    case 32: return launch<T, RB, 32>(tmap, sp, units, stream);
+    default: return launch<T, RB, 64>(tmap, sp, units, stream);
+  }
+}
+
+}  // namespace tcf
+
+bool window_scores_tc_supported(int B, int Hq, int Hkv, int L, int d, int w);
+
+// The grid barrier needs every CTA resident at once: units * chunks must fit the SM count.
+bool window_scores_fused_supported(int B, int Hq, int Hkv, int L, int d, int w) {
+  if (!window_scores_tc_supported(B, Hq, Hkv, L, d, w)) return false;
+  const tcf::Plan pl = tcf::make_plan(B, Hq, Hkv, L, w);
+  return B * Hkv * pl.nchunks <= sm_count();
+}
+
+size_t window_scores_fused_workspace_bytes(int B, int Hq, int Hkv, int L, int d, int w) {
+  if (!window_scores_tc_supported(B, Hq, Hkv, L, d, w)) return 0;
+  return tcf::make_plan(B, Hq, Hkv, L, w).stats_bytes + 256;
+}
+
+int window_scores_fused(const void* q, int64_t q_sb, int64_t q_sh, int64_t q_sl, const void* k, int64_t k_sb,
+                        int64_t k_sh, int64_t k_sl, int B, int Hq, int Hkv, int L, int d, int w, int dtype, int reduce,
+                        void* out_scores, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  using namespace tcf;
+  KVC_REQUIRE(window_scores_fused_supported(B, Hq, Hkv, L, d, w), KVC_ERR_UNSUPPORTED,
+              "fused tcgen05 scoring kernel does not cover this shape (Hq/Hkv=%d, w=%d, d=%d, units=%d)", Hq / Hkv, w, d,
+              B * Hkv);
+  KVC_REQUIRE(((q_sb | q_sh | q_sl) & 7) == 0 && (reinterpret_cast<uintptr_t>(q) & 15) == 0, KVC_ERR_UNSUPPORTED,
+              "tcgen05 scoring kernel: query rows must be 16-byte aligned");
+  KVC_REQUIRE(((k_sb | k_sh | k_sl) & 7) == 0 && (reinterpret_cast<uintptr_t>(k) & 15) == 0, KVC_ERR_UNSUPPORTED,
+              "tcgen05 scoring kernel: key rows must be 16-byte aligned (TMA)");
+  const Plan pl = make_plan(B, Hq, Hkv, L, w);
+  KVC_REQUIRE(workspace_bytes >= pl.stats_bytes + 256, KVC_ERR_WORKSPACE, "window_scores workspace: have %zu need %zu",
+              workspace_bytes, pl.stats_bytes + 256);
+  EncodeTiledFn enc = encode_fn();
+  KVC_REQUIRE(enc != nullptr, KVC_ERR_DEVICE, "cuTensorMapEncodeTiled is not available from this driver");
+  CUtensorMap tmap;
+  const cuuint64_t gdim[4] = {(cuuint64_t)d, (cuuint64_t)L, (cuuint64_t)Hkv, (cuuint64_t)B};
+  cuuint64_t gstr[3] = {(cuuint64_t)k_sl * 2, (cuuint64_t)k_sh * 2, (cuuint64_t)k_sb * 2};
+  if (Hkv == 1) gstr[1] = gstr[0] * (cuuint64_t)L;
+  if (B == 1) gstr[2] = gstr[0] * (cuuint64_t)L * (cuuint64_t)Hkv;
+  const cuuint32_t box[4] = {64, (cuuint32_t)kTile, 1, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult cr = enc(&tmap, dtype == KVC_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+                          4, const_cast<void*>(k), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  KVC_REQUIRE(cr == CUDA_SUCCESS, KVC_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
+  Params sp{};
+  sp.q = (const uint16_t*)q; sp.q_sb = q_sb; sp.q_sh = q_sh; sp.q_sl = q_sl;
+  sp.B = B; sp.Hq = Hq; sp.Hkv = Hkv; sp.L = L; sp.w = w; sp.groups = Hq / Hkv;
+  sp.chunk_tiles = pl.chunk_tiles; sp.nchunks = pl.nchunks;
+  sp.scale = 1.0f / sqrtf((float)d);
+  sp.reduce_mean = reduce == KVC_REDUCE_MEAN;
+  sp.stats = (float2*)workspace;
+  sp.sync_count = (unsigned*)((char*)workspace + pl.stats_bytes);
+  sp.out = (uint16_t*)out_scores;
+  const int units = B * Hkv;
+  if (dtype == KVC_BF16)
+    return pl.rb == 1 ? dispatch_w<Bf16, 1>(tmap, sp, units, stream) : dispatch_w<Bf16, 2>(tmap, sp, units, stream);
+  return pl.rb == 1 ? dispatch_w<Fp16, 1>(tmap, sp, units, stream) : dispatch_w<Fp16, 2>(tmap, sp, units, stream);
+}
+
+}  // namespace kvc

@@ -18,7 +18,7 @@ Q = torch.zeros(B, L, Hq, d, device=dev, dtype=torch.bfloat16)
 Q[:, L - w:] = torch.randn(B, w, Hq, d, generator=g, device=dev).to(torch.bfloat16)
 Q = Q.transpose(1, 2)
 cl = PyramidKVCluster(num_hidden_layers=32, window_size=w, max_capacity_prompt=2048, kernel_size=7, pooling="avgpool", layer_idx=layer)
-cl.score_impl = {"auto": 0, "mma": 1, "tc": 2}[impl]
+cl.score_impl = {"auto": 0, "mma": 1, "tc": 2, "fused": 3}[impl]
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 for _ in range(2):
     cl.update_kv(K, Q, V, None, 4)

@@ -29,7 +29,8 @@ SCORE_ULPS = 4.0
 SCORE_EXACT_FRAC = 0.90
 TIE_RTOL = {torch.bfloat16: 2.0 ** -5, torch.float16: 2.0 ** -8}
 
-IMPLS = [pytest.param(_native.IMPL_MMA_SYNC, id="mma_sync"), pytest.param(_native.IMPL_TCGEN05, id="tcgen05")]
+IMPLS = [pytest.param(_native.IMPL_MMA_SYNC, id="mma_sync"), pytest.param(_native.IMPL_TCGEN05, id="tcgen05"),
+         pytest.param(_native.IMPL_TCGEN05_FUSED, id="tcgen05_fused")]
 
 
 def dev():
