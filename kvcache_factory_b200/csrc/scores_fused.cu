@@ -15,6 +15,8 @@
 // Math, rounding points and operand roles are identical to scores_tc.cu.
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace kvc {
@@ -25,7 +27,8 @@ constexpr int kD = 128;
 constexpr int kHalfBytes = kTile * 64 * 2;
 constexpr int kTileBytes = 2 * kHalfBytes;
 constexpr int kNumBuf = 4;
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = 12;   // three epilogue warpgroups: 3 warps per scheduler hide the MUFU -> FADD latency chains
+constexpr int kNumWG = kEpiWarps / 4;
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kThreads = 32 * (2 + kEpiWarps);
 
@@ -95,6 +98,22 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
+// MUFU ping-pong between the two epilogue warpgroups.  The exp phase of a tile needs the MUFU pipe
+// (16 exp/clk/SM) for ~1100 cycles, the TMEM-load / rounding phase does not use it at all; left alone
+// both groups drift into doing the same phase at the same time.  A token handed over with named
+// barriers 2/3 lets one group run its exp phase while the other loads and converts its next tile.
+// pin(): zero-instruction register dependencies that stop the compiler from moving the exp work
+// out of the token's critical section.
+__device__ __forceinline__ void token_wait(int wg) {
+  if (wg == 0) asm volatile("bar.sync 2, 256;" ::: "memory"); else asm volatile("bar.sync 3, 256;" ::: "memory");
+}
+__device__ __forceinline__ void token_pass(int wg) {
+  if (wg == 0) asm volatile("bar.arrive 3, 256;" ::: "memory"); else asm volatile("bar.arrive 2, 256;" ::: "memory");
+}
+__device__ __forceinline__ void pin(uint32_t (&r)[64]) {
+#pragma unroll
+  for (int i = 0; i < 64; ++i) asm volatile("" : "+r"(r[i]));
+}
 __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3fffu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
@@ -111,8 +130,8 @@ struct Smem {
   static constexpr int kNumBars = 2 * kStages + 2 * kNumBuf + 1;
   static constexpr int kTmemPtrOff = kBarOff + kNumBars * 8;
   static constexpr int kCrowOff = (kTmemPtrOff + 4 + 15) & ~15;        // float[RB*128]
-  static constexpr int kXstatOff = kCrowOff + RB * 128 * 4;            // float2[RB][2][128]
-  static constexpr int kTotal = kXstatOff + RB * 2 * 128 * 8;
+  static constexpr int kXstatOff = kCrowOff + RB * 128 * 4;            // float2[RB][kNumWG][128]
+  static constexpr int kTotal = kXstatOff + RB * kNumWG * 128 * 8;
   static constexpr int kAlloc = kTotal + 1024;
 };
 
@@ -120,24 +139,30 @@ struct Smem {
 // roundings (GEMM result -> dtype, * 1/sqrt(d) in fp32 -> dtype): 64 packed pairs.
 template <typename T>
 __device__ __forceinline__ void load_round(uint32_t taddr, float scale, uint32_t (&r2)[64], uint32_t tempty_bar, int lane) {
-  uint32_t v[4][32];
-#pragma unroll
-  for (int cc = 0; cc < 4; ++cc) tmem_ld32(taddr + cc * 32, v[cc]);
-  tmem_ld_wait();
-  tc_fence_before();
-  __syncwarp();
-  if (lane == 0) mbar_arrive(tempty_bar);
   const float2 scale2 = make_float2(scale, scale);
+  // two halves of 64 columns: keeps the live register set small enough for 12 epilogue warps per SM
 #pragma unroll
-  for (int cc = 0; cc < 4; ++cc) {
-    uint32_t p1[16];
-    float2 f[16];
+  for (int half = 0; half < 2; ++half) {
+    uint32_t v[2][32];
+    tmem_ld32(taddr + half * 64, v[0]);
+    tmem_ld32(taddr + half * 64 + 32, v[1]);
+    tmem_ld_wait();
+    if (half == 1) {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar);
+    }
 #pragma unroll
-    for (int pi = 0; pi < 16; ++pi) p1[pi] = T::pack(__uint_as_float(v[cc][2 * pi]), __uint_as_float(v[cc][2 * pi + 1]));
+    for (int c2 = 0; c2 < 2; ++c2) {
+      uint32_t p1[16];
+      float2 f[16];
 #pragma unroll
-    for (int pi = 0; pi < 16; ++pi) f[pi] = __fmul2_rn(make_float2(T::lo(p1[pi]), T::hi(p1[pi])), scale2);
+      for (int pi = 0; pi < 16; ++pi) p1[pi] = T::pack(__uint_as_float(v[c2][2 * pi]), __uint_as_float(v[c2][2 * pi + 1]));
 #pragma unroll
-    for (int pi = 0; pi < 16; ++pi) r2[cc * 16 + pi] = T::pack(f[pi].x, f[pi].y);
+      for (int pi = 0; pi < 16; ++pi) f[pi] = __fmul2_rn(make_float2(T::lo(p1[pi]), T::hi(p1[pi])), scale2);
+#pragma unroll
+      for (int pi = 0; pi < 16; ++pi) r2[(half * 2 + c2) * 16 + pi] = T::pack(f[pi].x, f[pi].y);
+    }
   }
 }
 
@@ -240,8 +265,9 @@ window_score_fused_kernel(const __grid_constant__ CUtensorMap tmap_k, const Para
 
     // stage the Q block(s): canonical K-major SWIZZLE_128B layout, all chunks in flight
 #pragma unroll
-    for (int it = 0; it < RB * 128 * 16 / kEpiThreads; ++it) {
+    for (int it = 0; it < (RB * 128 * 16 + kEpiThreads - 1) / kEpiThreads; ++it) {
       const int e = et + it * kEpiThreads;
+      if (e >= RB * 128 * 16) break;
       const int rg = e >> 4, c16 = e & 15;
       const int rb = rg >> 7, r = rg & 127;
       const int hl = rg / W, i = rg % W;
@@ -262,7 +288,7 @@ window_score_fused_kernel(const __grid_constant__ CUtensorMap tmap_k, const Para
 #pragma unroll
     for (int rb = 0; rb < RB; ++rb) { m_run[rb] = -1e30f; z_run[rb] = 0.f; }
     int j = wg;
-    for (; j < n1 * RB; j += 2) {
+    for (; j < n1 * RB; j += kNumWG) {
       const int it = j / RB, rb = j % RB, buf = j % kNumBuf;
       const int key0 = tile_of(it) * kTile;
       mbar_wait(tfull(buf), (j / kNumBuf) & 1);
@@ -298,20 +324,25 @@ window_score_fused_kernel(const __grid_constant__ CUtensorMap tmap_k, const Para
 #pragma unroll
         for (int i = 0; i < 16; ++i) zacc[i & 3] = __fadd2_rn(zacc[i & 3], a[i]);
       }
-      const float2 z2 = __fadd2_rn(__fadd2_rn(zacc[0], zacc[1]), __fadd2_rn(zacc[2], zacc[3]));
+      float2 z2 = __fadd2_rn(__fadd2_rn(zacc[0], zacc[1]), __fadd2_rn(zacc[2], zacc[3]));
       m_run[rb] = m_new;
       z_run[rb] = z2.x + z2.y;
     }
 
     // ---------------- publish partials, grid barrier, fold all chunks into c_row ----------------
 #pragma unroll
-    for (int rb = 0; rb < RB; ++rb) xstat[(rb * 2 + wg) * 128 + r_loc] = make_float2(m_run[rb], z_run[rb]);
+    for (int rb = 0; rb < RB; ++rb) xstat[(rb * kNumWG + wg) * 128 + r_loc] = make_float2(m_run[rb], z_run[rb]);
     epi_sync();
     for (int r = et; r < RB * 128; r += kEpiThreads) {
       const int rb = r >> 7, rl = r & 127;
-      const float2 a = xstat[(rb * 2 + 0) * 128 + rl], c = xstat[(rb * 2 + 1) * 128 + rl];
-      const float mn = fmaxf(a.x, c.x);
-      const float z = a.y * fast_exp2((a.x - mn) * kLog2e) + c.y * fast_exp2((c.x - mn) * kLog2e);
+      float mn = -1e30f, z = 0.f;
+#pragma unroll
+      for (int g = 0; g < kNumWG; ++g) mn = fmaxf(mn, xstat[(rb * kNumWG + g) * 128 + rl].x);
+#pragma unroll
+      for (int g = 0; g < kNumWG; ++g) {
+        const float2 a = xstat[(rb * kNumWG + g) * 128 + rl];
+        z += a.y * fast_exp2((a.x - mn) * kLog2e);
+      }
       p.stats[((int64_t)unit * p.nchunks + chunk) * (RB * 128) + r] = make_float2(mn, z);
     }
     __threadfence();
@@ -359,7 +390,7 @@ window_score_fused_kernel(const __grid_constant__ CUtensorMap tmap_k, const Para
 
     // ---------------- pass 2: thread <-> key, columns are the stacked query rows ----------------
     constexpr int kHeadsPerBlk = 128 / W;
-    for (; j < (n1 + n2) * RB; j += 2) {
+    for (; j < (n1 + n2) * RB; j += kNumWG) {
       const int it = j / RB, rb = j % RB, buf = j % kNumBuf;
       const int key0 = tile_of(it) * kTile;
       mbar_wait(tfull(buf), (j / kNumBuf) & 1);
@@ -390,6 +421,7 @@ window_score_fused_kernel(const __grid_constant__ CUtensorMap tmap_k, const Para
           acc[col / W] = __fadd2_rn(acc[col / W], make_float2(T::lo(pp[i]), T::hi(pp[i])));
         }
       }
+#pragma unroll
       const int key = key0 + r_loc;
       if (key < nscore) {
 #pragma unroll
@@ -464,7 +496,11 @@ static int launch(const CUtensorMap& tmap, const Params& sp, int units, cudaStre
   attr[0].id = cudaLaunchAttributeCooperative;
   attr[0].val.cooperative = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  // KVC_FUSED_COOP=0: plain launch.  CTAs then trickle onto SMs as other streams' kernels (e.g. the
+  // asynchronous select/gather tail) retire instead of waiting for a fully free GPU; only safe when
+  // no second barrier-synchronised grid can run concurrently on the device.
+  static const bool coop = [] { const char* e = getenv("KVC_FUSED_COOP"); return !(e && e[0] == '0'); }();
+  cfg.numAttrs = coop ? 1 : 0;
   KVC_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, tmap, sp));
   return launch_status("window_score_fused_kernel");
 }

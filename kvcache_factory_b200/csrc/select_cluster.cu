@@ -159,35 +159,47 @@ topk_cluster_kernel(const uint16_t* __restrict__ scores, int n, int kernel_size,
   const int radius = POOL == KVC_POOL_NONE ? 0 : kernel_size / 2;
   const int s0 = (int)crank * SL;
 
-  // ---- 1. stage [s0-kHalo, s0+SL+kHalo) and pool ------------------------------------------------
-  {
-    // all E+1 loads of a thread are issued before the first store (the row comes from L2 / HBM)
-    uint16_t raw[E + 1];
-#pragma unroll
-    for (int it = 0; it <= E; ++it) {
-      const int q = tid + it * kThreads, j = s0 - kHalo + q;
-      raw[it] = (q < SL + 2 * kHalo && j >= 0 && j < n) ? __ldg(srow + j) : (uint16_t)0;
-    }
-#pragma unroll
-    for (int it = 0; it <= E; ++it) {
-      const int q = tid + it * kThreads;
-      if (q < SL + 2 * kHalo) stage[q + 2 * (q / E)] = raw[it];
-    }
-  }
-  __syncthreads();
+  // ---- 1. load this thread's E scores (+ pooling halo) straight into registers, pool -------------
+  // Own elements: 8-element (16-byte) vector loads when the row allows it -- a warp then reads one
+  // contiguous span; the 2*kHalo halo elements are the neighbours' own elements (L1 hits).
   const int j0 = s0 + tid * E;
   uint32_t keys[E];
   float part_all = 0.f;
   {
+    uint16_t raw[E + 2 * kHalo] = {};
+    const bool vec =(n & 7) == 0 && (E & 7) == 0 && (reinterpret_cast<uintptr_t>(srow) & 15) == 0;
+    if (vec) {
+#pragma unroll
+      for (int v8 = 0; v8 < E / 8; ++v8) {
+        uint4 q = make_uint4(0u, 0u, 0u, 0u);
+        if (j0 + v8 * 8 < n) q = __ldg(reinterpret_cast<const uint4*>(srow + j0 + v8 * 8));
+        const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          raw[kHalo + v8 * 8 + 2 * i] = (uint16_t)(w4[i] & 0xffffu);
+          raw[kHalo + v8 * 8 + 2 * i + 1] = (uint16_t)(w4[i] >> 16);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < E; ++i) raw[kHalo + i] = j0 + i < n ? __ldg(srow + j0 + i) : (uint16_t)0;
+    }
+    if (POOL != KVC_POOL_NONE) {
+#pragma unroll
+      for (int i = 0; i < kHalo; ++i) {
+        const int jl = j0 - kHalo + i, jr = j0 + E + i;
+        raw[i] = (jl >= 0 && jl < n) ? __ldg(srow + jl) : (uint16_t)0;
+        raw[kHalo + E + i] = jr < n ? __ldg(srow + jr) : (uint16_t)0;
+      }
+    }
     float f[E + 2 * kHalo];
     uint32_t kk[E + 2 * kHalo];
 #pragma unroll
     for (int i = 0; i < E + 2 * kHalo; ++i) {
-      const int q = tid * E + i, j = s0 - kHalo + q;
-      const uint16_t raw = stage[q + 2 * (q / E)];
+      const int j = j0 - kHalo + i;
       const bool in = j >= 0 && j < n;
-      if (POOL == KVC_POOL_AVG) f[i] = in ? T::to_float(raw) : 0.f;
-      else kk[i] = in ? float16_bits_to_key(raw) : 0u;
+      if (POOL == KVC_POOL_AVG) f[i] = in ? T::to_float(raw[i]) : 0.f;
+      else kk[i] = in ? float16_bits_to_key(raw[i]) : 0u;
     }
 #pragma unroll
     for (int i = 0; i < E; ++i) {
