@@ -203,6 +203,10 @@ def run_ours(args, wl):
         raise SystemExit("bench.py --impl ours needs a CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # One process per GPU and one stream of scoring kernels: the fused scoring kernel may be launched
+    # without the cooperative attribute so that its CTAs start while the previous layer's asynchronous
+    # select/gather tail is still draining (see scores_fused.cu).  Must be set before the library loads.
+    os.environ.setdefault("KVC_FUSED_COOP", "0")
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
@@ -292,29 +296,38 @@ def run_ours(args, wl):
     ms_per_step = ms / args.steps
     value = world * B * L / (ms_per_step * 1e-3)
 
-    # ---- phase split inside a timed region (CUDA events around each C-ABI call, eager launches) ----
-    phase = {"scores": [], "select": [], "gather": []}
-    ev = []
-    for _ in range(max(1, min(args.steps, 3))):
-        for layer in range(nl):
-            cl = clusters[layer]
-            n_keep = kept_rows(wl, layer) - w
-            marks = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-            marks[0].record()
-            sc = _native.window_scores(Qs[layer], Ks[layer], w, "sum", impl)
-            marks[1].record()
-            idx, _, _ = _native.pool_topk(sc, wl["kernel"], wl["pooling"], n_keep)
-            marks[2].record()
-            _native.gather_dense(Ks[layer], Vs[layer], idx, Hq, n_keep, w)
-            marks[3].record()
-            ev.append((layer, marks))
-    torch.cuda.synchronize()
-    per_layer = {k: [[] for _ in range(nl)] for k in phase}
-    for layer, m in ev:
-        per_layer["scores"][layer].append(m[0].elapsed_time(m[1]))
-        per_layer["select"][layer].append(m[1].elapsed_time(m[2]))
-        per_layer["gather"][layer].append(m[2].elapsed_time(m[3]))
-    tot = {k: sum(statistics.mean(x) for x in per_layer[k]) for k in per_layer}  # ms per step
+    # ---- per-kernel time, live: each phase's 32 launches (one per layer) replayed as its own CUDA
+    # graph and bracketed by CUDA events on the launching stream (no host gaps inside the bracket) ----
+    def phase_graph(fn):
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        g_ = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            fn()
+            with torch.cuda.graph(g_, stream=side):
+                keep = fn()
+        torch.cuda.current_stream().wait_stream(side)
+        return g_, keep
+
+    def time_graph(g_, reps):
+        g_.replay()
+        torch.cuda.synchronize()
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            g_.replay()
+        b_.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b_) / reps
+
+    keeps = [kept_rows(wl, l) - w for l in range(nl)]
+    g_sc, scs = phase_graph(lambda: [_native.window_scores(Qs[l], Ks[l], w, "sum", impl) for l in range(nl)])
+    g_se, idxs = phase_graph(lambda: [_native.pool_topk(scs[l], wl["kernel"], wl["pooling"], keeps[l])[0]
+                                      for l in range(nl)])
+    g_ga, _outs = phase_graph(lambda: [_native.gather_dense(Ks[l], Vs[l], idxs[l], Hq, keeps[l], w) for l in range(nl)])
+    reps = max(3, min(args.steps, 10))
+    tot = {"scores": time_graph(g_sc, reps), "select": time_graph(g_se, reps), "gather": time_graph(g_ga, reps)}
+    del g_sc, g_se, g_ga, scs, idxs, _outs
     dominant = max(tot, key=tot.get)
     sb = sum(alg_bytes_layer(wl, l)[0] for l in range(nl))
     gb = sum(alg_bytes_layer(wl, l)[1] for l in range(nl))

@@ -10,10 +10,12 @@ from .pyramidkv_utils import (  # noqa: F401
     AdaKVCluster,
     DynamicCacheSplitHeadFlatten,
     H2OKVCluster,
+    HeadKVCluster,
     PyramidKVCluster,
     SnapKVCluster,
     StreamingLLMKVCluster,
     init_adakv,
+    init_headkv,
     init_H2O,
     init_pyramidkv,
     init_snapkv,
@@ -24,7 +26,7 @@ from .pyramidkv_utils import (  # noqa: F401
 )
 
 __all__ = [
-    "AdaKVCluster", "DynamicCacheSplitHeadFlatten", "H2OKVCluster", "PyramidKVCluster", "SnapKVCluster",
+    "AdaKVCluster", "DynamicCacheSplitHeadFlatten", "H2OKVCluster", "HeadKVCluster", "init_headkv", "PyramidKVCluster", "SnapKVCluster",
     "StreamingLLMKVCluster", "init_adakv", "init_H2O", "init_pyramidkv", "init_snapkv", "init_StreamingLLM",
     "pyramid_budget", "repeat_kv", "wait_for_compression",
 ]

@@ -375,6 +375,61 @@ class AdaKVCluster:
         return flat_k, flat_v
 
 
+class HeadKVCluster(AdaKVCluster):
+    """Reference ``HeadKVCluster`` (``pyramidkv_utils.py:760-878``): AdaKV's flattened layout with
+    per-head capacities supplied by the caller (``head_capacity[layer_idx][head]``, computed from the
+    head-importance file at ``run_longbench.py:225-234``) instead of the global allocation."""
+
+    def __init__(self, window_size=32, kernel_size=7, pooling='maxpool', max_capacity_prompt=None, layer_idx=None,
+                 num_hidden_layers=None, head_capacity=None):
+        self.window_size = window_size
+        self.kernel_size = kernel_size
+        self.pooling = pooling
+        self.base_capacity = max_capacity_prompt - window_size
+        self.head_adaptive_capacity = head_capacity
+        self.num_hidden_layers = num_hidden_layers
+        self.layer_idx = layer_idx
+
+        self.head_lens = None
+        self.max_seqlen_k = 0
+        self.klen_sum = 0
+        self.cu_klen = 0
+        self.cu_offset = None
+        self.cu_headlens = None
+
+    def update_kv(self, key_states, query_states, value_states):
+        device = key_states.device
+        bsz, num_heads, q_len, head_dim = query_states.shape
+        _kv_heads(key_states, query_states, num_heads // key_states.shape[1])
+        w = self.window_size
+        if self.pooling not in ("avgpool", "maxpool"):
+            raise ValueError("Pooling method not supported")
+        n = q_len - w
+        if self.base_capacity > n:                                   # :834-837 flatten only
+            head_lens = torch.full((num_heads,), q_len, dtype=torch.int32, device=device)
+            cu_klen = torch.arange(0, num_heads + 1, dtype=torch.int32, device=device) * q_len
+            self._init_metadata(device, num_heads, head_lens, cu_klen, q_len * num_heads, q_len)
+            k_all, v_all = N.gather_dense(key_states, value_states, None, num_heads, n, w)
+            return k_all.reshape(-1, head_dim), v_all.reshape(-1, head_dim)
+        assert bsz == 1                                              # :845
+        caps = [min(int(c), n) for c in self.head_adaptive_capacity[self.layer_idx]][:num_heads]
+        cap = torch.tensor(caps, dtype=torch.int32, device=device)   # slicing [:cap] clamps at the row length
+        max_cap = max(caps)
+        scores = N.window_scores(query_states, key_states, w, "mean", self.score_impl)
+        idx, pooled, _ = N.pool_topk(scores, self.kernel_size, self.pooling, max_cap, k_per_row=cap,
+                                     want_pooled=self.keep_debug)
+        idx = idx.view(num_heads, max_cap)
+        head_lens = cap + w
+        cu_klen = torch.zeros(num_heads + 1, dtype=torch.int32, device=device)
+        cu_klen[1:] = head_lens.cumsum(0)
+        klen_sum = sum(caps) + num_heads * w
+        flat_k, flat_v = N.gather_varlen(key_states, value_states, idx, cap, cu_klen, num_heads, w, max_cap, klen_sum)
+        self._init_metadata(device, num_heads, head_lens, cu_klen, klen_sum, max_cap + w)
+        if self.keep_debug:
+            self.debug = dict(scores=scores, pooled=pooled, cap=cap, indices=idx)
+        return flat_k, flat_v
+
+
 class DynamicCacheSplitHeadFlatten:
     """Flattened per-layer KV store of AdaKV (reference ``pyramidkv_utils.py:28-102``).
 
@@ -496,3 +551,17 @@ def init_adakv(self):
             window_size=self.config.window_size, max_capacity_prompt=self.config.max_capacity_prompt,
             kernel_size=self.config.kernel_size, pooling=self.config.pooling, floor=self.config.floor,
             normalize=self.config.normalize)
+
+
+def init_headkv(self):
+    """Reference ``init_headkv`` (``pyramidkv_utils.py:1062-1085``): needs ``config.head_capacity``."""
+    if not hasattr(self, "kv_cluster"):
+        _defaults(self.config, window_size=32, max_capacity_prompt=2048, kernel_size=5, pooling='maxpool')
+        if not hasattr(self.config, 'head_capacity'):
+            raise ValueError("Must have head_capacity")
+    if not hasattr(self, "kv_cluster"):                              # built once (:1076)
+        self.kv_cluster = HeadKVCluster(
+            num_hidden_layers=self.config.num_hidden_layers, layer_idx=self.layer_idx,
+            window_size=self.config.window_size, max_capacity_prompt=self.config.max_capacity_prompt,
+            kernel_size=self.config.kernel_size, pooling=self.config.pooling,
+            head_capacity=self.config.head_capacity)

@@ -348,3 +348,29 @@ def check_index_sets(pooled: torch.Tensor, idx_test: torch.Tensor, k: int, rtol:
                 bad = sel[P[b, h, sel] < t - margin][:5].tolist()
                 return False, f"(b={b},h={h}) selected below threshold, e.g. {bad}"
     return True, "ok"
+
+
+# --------------------------------------------------------------------------------------------
+# f1  HeadKV (AdaKV layout, externally supplied capacities)
+# --------------------------------------------------------------------------------------------
+def headkv_update_kv(K, Q, V, head_capacity, layer_idx, window_size=32, kernel_size=7, pooling="maxpool",
+                     max_capacity_prompt=2048):
+    """``HeadKVCluster.update_kv`` (``pyramidkv_utils.py:808-878``): per head keep the first
+    ``head_capacity[layer_idx][h]`` positions of the descending sort of the pooled window-mean scores."""
+    B, Hq, L, d = Q.shape
+    w = window_size
+    base = max_capacity_prompt - w
+    Kr, Vr = _expand(K, V, Hq)
+    pooled = adakv_scores(K, Q, w, kernel_size, pooling)
+    if base > pooled.size(-1):
+        return Kr.reshape(-1, d), Vr.reshape(-1, d), varlen_metadata([L] * Hq), pooled, None
+    assert B == 1
+    _, sorted_idx = pooled.sort(dim=-1, descending=True)
+    ks, vs, lens, picks = [], [], [], []
+    for h in range(Hq):
+        sel = sorted_idx[0, h, : int(head_capacity[layer_idx][h])]
+        picks.append(sel)
+        lens.append(int(sel.numel()) + w)
+        ks.append(torch.cat([Kr[0, h, :-w][sel], Kr[0, h, -w:]], dim=0))
+        vs.append(torch.cat([Vr[0, h, :-w][sel], Vr[0, h, -w:]], dim=0))
+    return torch.cat(ks, 0), torch.cat(vs, 0), varlen_metadata(lens), pooled, picks

@@ -65,6 +65,9 @@ CASES = {
     "adakv_fp16_nonorm":  dict(method="adakv", B=1, Hq=4, Hkv=4, L=512, d=128, dtype="fp16", dist="peaked",
                                knobs=dict(window_size=16, kernel_size=5, pooling="avgpool", max_capacity_prompt=96,
                                           floor=0.5, normalize=False)),
+    "headkv_bf16":        dict(method="headkv", B=1, Hq=8, Hkv=2, L=768, d=128, dtype="bf16", dist="peaked",
+                               knobs=dict(window_size=32, kernel_size=7, pooling="maxpool", max_capacity_prompt=128,
+                                          layer_idx=1, head_capacity=[[96] * 8, [10, 200, 96, 1, 736, 64, 300, 50]])),
     "adakv_nocompress":   dict(method="adakv", B=1, Hq=4, Hkv=2, L=96, d=128, dtype="bf16", dist="normal",
                                knobs=dict(window_size=32, kernel_size=7, pooling="maxpool", max_capacity_prompt=128,
                                           floor=0.2, normalize=True)),
@@ -129,8 +132,8 @@ def run_case(ref, name: str, c: dict) -> dict:
         elif m == "streamingllm":
             cl = ref.StreamingLLMKVCluster(**kn)
             Kc, Vc = cl.update_kv(Kr, Q, Vr, None, shape.groups)
-        elif m == "adakv":
-            cl = ref.AdaKVCluster(**kn)
+        elif m in ("adakv", "headkv"):
+            cl = ref.AdaKVCluster(**kn) if m == "adakv" else ref.HeadKVCluster(**kn)
             Kc, Vc = cl.update_kv(Kr, Q, Vr)
             for a in ("head_lens", "cu_klen", "cu_headlens", "cu_qlen", "cu_offset", "cu_head_offset",
                       "layer_qlens"):
@@ -156,7 +159,13 @@ def main() -> None:
         import pyramidkv.pyramidkv_utils as ref  # the unmodified reference
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     manifest = {}
+    only = set(sys.argv[1:])
+    if only:   # add / refresh selected cases only, keep the rest of the manifest
+        with open(os.path.join(OUT, "manifest.json")) as f:
+            manifest = json.load(f)
     for name, c in CASES.items():
+        if only and name not in only:
+            continue
         res = run_case(ref, name, c)
         np.savez_compressed(os.path.join(OUT, name + ".npz"), **res)
         manifest[name] = {k: v for k, v in c.items()}

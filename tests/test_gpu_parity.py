@@ -403,6 +403,35 @@ def test_adakv_matches_reference_vectors(name):
         assert torch.equal(fk[cu[h]:cu[h + 1]].cpu(), rows_k) and torch.equal(fv[cu[h]:cu[h + 1]].cpu(), rows_v)
 
 
+@pytest.mark.parametrize("name", golden_cases("headkv"))
+def test_headkv_matches_reference_vectors(name):
+    from kvcache_factory_b200 import HeadKVCluster
+    c, z, (Q, K, V) = load_golden(name)
+    kn = dict(c["knobs"])
+    dtype = DTYPES[c["dtype"]]
+    w, H = kn["window_size"], c["Hq"]
+    cl = HeadKVCluster(**kn)
+    cl.keep_debug = True
+    fk, fv = cl.update_kv(K.to(dev()), Q.to(dev()), V.to(dev()))
+    torch.cuda.synchronize()
+    # capacities are inputs here, so the metadata is exact
+    for a in ("head_lens", "cu_klen", "cu_headlens", "cu_qlen", "cu_offset", "cu_head_offset", "layer_qlens"):
+        assert np.array_equal(getattr(cl, a).cpu().numpy(), z["meta_" + a]), a
+    assert [cl.klen_sum, cl.qlen_sum, cl.max_seqlen_k] == z["meta_scalars"].tolist()
+    pooled_ref = from_bits(z["pooled"], dtype)
+    g = c["Hq"] // c["Hkv"]
+    Kr, Vr = O.repeat_kv(K, g), O.repeat_kv(V, g)
+    idx = cl.debug["indices"].cpu().long()
+    cu = cl.cu_klen.cpu().numpy()
+    for h in range(H):
+        cap = int(cl.head_lens[h]) - w
+        sel = idx[h, :cap]
+        ok, msg = O.check_index_sets(pooled_ref[:, h:h + 1], sel.view(1, 1, -1), cap, rtol=TIE_RTOL[dtype])
+        assert ok, f"head {h}: {msg}"
+        assert torch.equal(fk[cu[h]:cu[h + 1]].cpu(), torch.cat([Kr[0, h, :-w][sel], Kr[0, h, -w:]], 0))
+        assert torch.equal(fv[cu[h]:cu[h + 1]].cpu(), torch.cat([Vr[0, h, :-w][sel], Vr[0, h, -w:]], 0))
+
+
 # ------------------------------------------------------------------------------------------------
 # BASELINE sizes: size-independent properties
 # ------------------------------------------------------------------------------------------------

@@ -57,6 +57,17 @@ def test_adakv_matches_reference_vectors(name):
     assert np.array_equal(to_bits(flatV), z["V_out"])
 
 
+@pytest.mark.parametrize("name", golden_cases("headkv"))
+def test_headkv_matches_reference_vectors(name):
+    c, z, (Q, K, V) = load_golden(name)
+    kn = dict(c["knobs"])
+    flatK, flatV, meta, pooled, picks = O.headkv_update_kv(K, Q, V, kn.pop("head_capacity"), kn.pop("layer_idx"), **kn)
+    assert np.array_equal(to_bits(pooled), z["pooled"])
+    for a in ("head_lens", "cu_klen", "cu_headlens"):
+        assert np.array_equal(meta[a], z["meta_" + a]), a
+    assert np.array_equal(to_bits(flatK), z["K_out"]) and np.array_equal(to_bits(flatV), z["V_out"])
+
+
 def test_pyramid_budget_schedule_matches_survey_numbers():
     # cfg-2 budgets 3932 - 123*l, sum of kept rows 65 840; cfg-5 steps 48.
     b = [O.pyramidkv_budget(32768, 32, 2048, 32, l) for l in range(32)]
