@@ -351,14 +351,17 @@ topk_cluster_kernel(const uint16_t* __restrict__ scores, int n, int kernel_size,
     const int V = (k + kThreads - 1) / kThreads;          // slots per thread (<= 8)
     const int per_warp = V * 32;                          // warp w owns elements [w*per_warp, (w+1)*per_warp)
     int cur = 0;
-    for (int pass = 0; pass < 2; ++pass) {
+    // LSD radix sort on rk = kmax - key (ascending rk == descending key); the winners' keys usually
+    // span fewer than 256 values, then one pass sorts them completely
+    const int npass = (kmax - thr_key) < 256 ? 1 : 2;
+    for (int pass = 0; pass < npass; ++pass) {
 #pragma unroll
       for (int i = lane; i < 256; i += 32) wh[i] = 0;
       __syncwarp();
       // per-warp digit totals (elements of a warp's run are visited in order, so ranks are stable)
       for (int v = 0; v < V; ++v) {
         const int o = wid * per_warp + v * 32 + lane;
-        if (o < k) atomicAdd(&wh[255 - (int)((skey[cur][o] >> (8 * pass)) & 255u)], 1);
+        if (o < k) atomicAdd(&wh[((kmax - (int)skey[cur][o]) >> (8 * pass)) & 255], 1);
       }
       __syncthreads();
       // digit bases: thread t < 256 <-> digit t; exclusive scan over digits of the per-digit totals,
@@ -381,8 +384,8 @@ topk_cluster_kernel(const uint16_t* __restrict__ scores, int n, int kernel_size,
         const bool in = o < k;
         const uint16_t key = in ? skey[cur][o] : (uint16_t)0;
         const uint32_t idx = in ? sidx[cur][o] : 0u;
-        // lanes past the end use digit 255 of the LAST pass ordering: they come after every real element
-        const int dgt = in ? 255 - (int)((key >> (8 * pass)) & 255u) : 255;
+        // lanes past the end use the last digit: they rank after every real element of the warp's run
+        const int dgt = in ? ((kmax - (int)key) >> (8 * pass)) & 255 : 255;
         const int dst = warp_rank_digit(wh, dgt, lane);
         if (in) { skey[cur ^ 1][dst] = key; sidx[cur ^ 1][dst] = idx; }
       }
