@@ -260,7 +260,10 @@ def run_ours(args, wl):
     graph = None
     if not args.no_graph:
         graph = torch.cuda.CUDAGraph()
-        side = torch.cuda.Stream()
+        # the scoring kernels run on a HIGH-priority stream, the select/gather tails on the library's
+        # default-priority side stream: the block scheduler then places the next layer's scoring CTAs
+        # first and lets the tail fill what is left of each SM (kernel-node priorities are captured)
+        side = torch.cuda.Stream(priority=-1)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             step()

@@ -51,6 +51,12 @@ struct Bf16 {
   }
   __device__ static __forceinline__ float lo(uint32_t p) { return __uint_as_float(p << 16); }
   __device__ static __forceinline__ float hi(uint32_t p) { return __uint_as_float(p & 0xffff0000u); }
+  // round to bf16, result kept in fp32 format: one F2FP with a zero partner (no unpack needed)
+  __device__ static __forceinline__ float rnd(float x) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(x), "f"(0.f));
+    return __uint_as_float(r);
+  }
   __device__ static __forceinline__ uint32_t max2(uint32_t a, uint32_t b) {
     __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
     return *reinterpret_cast<uint32_t*>(&r);
@@ -75,6 +81,7 @@ struct Fp16 {
   __device__ static __forceinline__ float hi(uint32_t p) {
     return __high2float(*reinterpret_cast<__half2*>(&p));
   }
+  __device__ static __forceinline__ float rnd(float x) { return __half2float(__float2half_rn(x)); }
   __device__ static __forceinline__ uint32_t max2(uint32_t a, uint32_t b) {
     __half2 r = __hmax2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b));
     return *reinterpret_cast<uint32_t*>(&r);

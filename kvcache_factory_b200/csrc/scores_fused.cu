@@ -27,7 +27,12 @@ constexpr int kD = 128;
 constexpr int kHalfBytes = kTile * 64 * 2;
 constexpr int kTileBytes = 2 * kHalfBytes;
 constexpr int kNumBuf = 4;
-constexpr int kEpiWarps = 12;   // three epilogue warpgroups: 3 warps per scheduler hide the MUFU -> FADD latency chains
+// Four epilogue warpgroups; warpgroup g owns columns [32g, 32g+32) of EVERY accumulator tile.  A tile's
+// TMEM buffer is therefore drained by all 16 warps at once and handed back after one 32-column load
+// each, which keeps the MMA issuer up to three tiles ahead of the slowest warp (with one tile per
+// warpgroup the buffers were held ~4x longer and the epilogue starved ~30% of the time); 4 warps per
+// scheduler cover the TMEM-load and MUFU latencies.
+constexpr int kEpiWarps = 16;
 constexpr int kNumWG = kEpiWarps / 4;
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kThreads = 32 * (2 + kEpiWarps);
@@ -40,7 +45,6 @@ struct Params {
   int reduce_mean;
   float2* stats;        // [units][nchunks][RB*128]
   uint16_t* out;        // [B,Hq,L-w]
-  unsigned* sync_count; // grid barrier counter, zeroed before the launch
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -74,6 +78,11 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tma
       ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -98,28 +107,38 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
-// MUFU ping-pong between the two epilogue warpgroups.  The exp phase of a tile needs the MUFU pipe
-// (16 exp/clk/SM) for ~1100 cycles, the TMEM-load / rounding phase does not use it at all; left alone
-// both groups drift into doing the same phase at the same time.  A token handed over with named
-// barriers 2/3 lets one group run its exp phase while the other loads and converts its next tile.
-// pin(): zero-instruction register dependencies that stop the compiler from moving the exp work
-// out of the token's critical section.
-__device__ __forceinline__ void token_wait(int wg) {
-  if (wg == 0) asm volatile("bar.sync 2, 256;" ::: "memory"); else asm volatile("bar.sync 3, 256;" ::: "memory");
-}
-__device__ __forceinline__ void token_pass(int wg) {
-  if (wg == 0) asm volatile("bar.arrive 3, 256;" ::: "memory"); else asm volatile("bar.arrive 2, 256;" ::: "memory");
-}
-__device__ __forceinline__ void pin(uint32_t (&r)[64]) {
-#pragma unroll
-  for (int i = 0; i < 64; ++i) asm volatile("" : "+r"(r[i]));
-}
 __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3fffu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
 __device__ __forceinline__ uint32_t instr_desc(int fmt, int M, int N) {
   return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+
+// Optional timeline (developer tool, `make TRACE=1`): 16 globaltimer stamps per CTA, read back by
+// kvc_debug_ftrace().  Compiled out of the shipped library.
+#ifdef KVC_TRACE
+__device__ long long g_trace[160 * 16];
+__device__ unsigned g_tile_trace[4][64][8];  // CTAs 0, 1, 70, 143: per tile SM-clock stamps {tma issue, kfull seen, tempty seen, mma committed, epi got tile, epi loaded, epi done}
+__shared__ unsigned s_tile_trace[64][8];
+__device__ __forceinline__ void tile_stamp(int j, int slot) {
+  if (j < 64) s_tile_trace[j][slot] = (unsigned)clock64();
+}
+#define KVC_TILE_STAMP(cond, j, slot) do { if (cond) tile_stamp(j, slot); } while (0)
+__device__ __forceinline__ void stamp(int slot) {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  g_trace[(blockIdx.y * gridDim.x + blockIdx.x) * 16 + slot] = t;
+}
+#define KVC_STAMP(cond, slot) do { if (cond) stamp(slot); } while (0)
+#else
+#define KVC_STAMP(cond, slot) do { } while (0)
+#define KVC_TILE_STAMP(cond, j, slot) do { } while (0)
+#endif
+
+// Grid-barrier state (per device, zero at module load, self-resetting).  One barrier kernel runs at a
+// time on a device: the cooperative launch admits a grid only when all of its CTAs fit, and two such
+// grids (one CTA per SM each) never fit together.
+__device__ unsigned g_bar_count = 0, g_bar_gen = 0;
 
 template <int RB>
 struct Smem {
@@ -135,33 +154,69 @@ struct Smem {
   static constexpr int kAlloc = kTotal + 1024;
 };
 
-// TMEM accumulator (4 x 32 columns) -> registers, hand the buffer back, apply the reference's two
-// roundings (GEMM result -> dtype, * 1/sqrt(d) in fp32 -> dtype): 64 packed pairs.
-template <typename T>
-__device__ __forceinline__ void load_round(uint32_t taddr, float scale, uint32_t (&r2)[64], uint32_t tempty_bar, int lane) {
+// Lazy running maximum of pass 1: the exponentials of a row are taken relative to a reference m_ref
+// that is only raised when a 32-key chunk exceeds it by more than kTau (a warp-uniform, rare branch);
+// (m_ref, Z) still represents Z * e^m_ref exactly, so the folded statistics are unchanged while the
+// per-chunk rescale (one MUFU + a dependent multiply per row per chunk) disappears from the hot loop.
+constexpr float kTau = 6.0f;
+
+// Pass 1, one chunk of 32 keys of this thread's query row: the reference's two roundings (GEMM result
+// -> dtype, * 1/sqrt(d) in fp32 -> dtype), lazy max, Z += sum exp(x - m_ref).
+template <typename T, bool MASK>
+__device__ __forceinline__ void p1_chunk(const uint32_t (&v)[32], float scale, float& m_ref, float2 (&zacc)[4], int key0,
+                                         int last_key) {
   const float2 scale2 = make_float2(scale, scale);
-  // two halves of 64 columns: keeps the live register set small enough for 12 epilogue warps per SM
+  const float2 l2e2 = make_float2(kLog2e, kLog2e);
+  uint32_t r2[16];
 #pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    uint32_t v[2][32];
-    tmem_ld32(taddr + half * 64, v[0]);
-    tmem_ld32(taddr + half * 64 + 32, v[1]);
-    tmem_ld_wait();
-    if (half == 1) {
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar);
+  for (int i = 0; i < 16; ++i) {
+    const float2 f = __fmul2_rn(make_float2(T::rnd(__uint_as_float(v[2 * i])), T::rnd(__uint_as_float(v[2 * i + 1]))), scale2);
+    r2[i] = T::pack(f.x, f.y);
+  }
+  if (MASK) {  // chunk touches the w x w causal block or the ragged end
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int key = key0 + 2 * i;
+      if (key > last_key) r2[i] = (r2[i] & 0xffff0000u) | (T::kNegInfPair & 0xffffu);
+      if (key + 1 > last_key) r2[i] = (r2[i] & 0x0000ffffu) | (T::kNegInfPair & 0xffff0000u);
     }
+  }
+  uint32_t pm = r2[0];
 #pragma unroll
-    for (int c2 = 0; c2 < 2; ++c2) {
-      uint32_t p1[16];
-      float2 f[16];
+  for (int i = 1; i < 16; ++i) pm = T::max2(pm, r2[i]);
+  const float cm = fmaxf(T::lo(pm), T::hi(pm));
+  if (__any_sync(0xffffffffu, cm > m_ref + kTau)) {
+    const float m_new = cm > m_ref + kTau ? cm : m_ref;
+    const float sc = fast_exp2((m_ref - m_new) * kLog2e);
+    const float2 sc2 = make_float2(sc, sc);
 #pragma unroll
-      for (int pi = 0; pi < 16; ++pi) p1[pi] = T::pack(__uint_as_float(v[c2][2 * pi]), __uint_as_float(v[c2][2 * pi + 1]));
+    for (int a = 0; a < 4; ++a) zacc[a] = __fmul2_rn(zacc[a], sc2);
+    m_ref = m_new;
+  }
+  const float2 ml2 = make_float2(-m_ref * kLog2e, -m_ref * kLog2e);
 #pragma unroll
-      for (int pi = 0; pi < 16; ++pi) f[pi] = __fmul2_rn(make_float2(T::lo(p1[pi]), T::hi(p1[pi])), scale2);
+  for (int i = 0; i < 16; ++i) {
+    const float2 a = __ffma2_rn(make_float2(T::lo(r2[i]), T::hi(r2[i])), l2e2, ml2);
+    zacc[i & 3] = __fadd2_rn(zacc[i & 3], make_float2(fast_exp2(a.x), fast_exp2(a.y)));
+  }
+}
+
+// Pass 2, one chunk of 32 stacked query rows of this thread's key: the same two roundings,
+// p = exp2(x*log2e + c_row) rounded to dtype (softmax output), summed per head in fp32.
+template <typename T, int W>
+__device__ __forceinline__ void p2_chunk(const uint32_t (&v)[32], float scale, const float* cr, float2 (&acc)[32 / W]) {
+  const float2 scale2 = make_float2(scale, scale);
+  const float2 l2e2 = make_float2(kLog2e, kLog2e);
 #pragma unroll
-      for (int pi = 0; pi < 16; ++pi) r2[(half * 2 + c2) * 16 + pi] = T::pack(f[pi].x, f[pi].y);
+  for (int q4 = 0; q4 < 8; ++q4) {
+    const float4 c4 = *reinterpret_cast<const float4*>(cr + q4 * 4);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int i = 2 * q4 + h;
+      float2 f = __fmul2_rn(make_float2(T::rnd(__uint_as_float(v[2 * i])), T::rnd(__uint_as_float(v[2 * i + 1]))), scale2);
+      f = __ffma2_rn(make_float2(T::rnd(f.x), T::rnd(f.y)), l2e2, h == 0 ? make_float2(c4.x, c4.y) : make_float2(c4.z, c4.w));
+      const float2 e = make_float2(T::rnd(fast_exp2(f.x)), T::rnd(fast_exp2(f.y)));
+      acc[(2 * i) / W] = __fadd2_rn(acc[(2 * i) / W], e);
     }
   }
 }
@@ -197,9 +252,10 @@ window_score_fused_kernel(const __grid_constant__ CUtensorMap tmap_k, const Para
   float* crow = reinterpret_cast<float*>(smem + SM::kCrowOff);
   float2* xstat = reinterpret_cast<float2*>(smem + SM::kXstatOff);
 
+  KVC_STAMP(tid == 0, 0);
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(kfull(s), 1); mbar_init(kempty(s), 1); }
-    for (int i = 0; i < kNumBuf; ++i) { mbar_init(tfull(i), 1); mbar_init(tempty(i), 4); }
+    for (int i = 0; i < kNumBuf; ++i) { mbar_init(tfull(i), 1); mbar_init(tempty(i), kEpiWarps); }
     mbar_init(qbar, kEpiThreads);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -216,44 +272,57 @@ window_score_fused_kernel(const __grid_constant__ CUtensorMap tmap_k, const Para
 
   if (warp == 0) {
     // ===== TMA producer: one stream of n1 + n2 tiles =====
-    if (lane == 0) {
-      for (int it = 0; it < n1 + n2; ++it) {
-        const int s = it % S;
-        mbar_wait(kempty(s), ((it / S) & 1) ^ 1);
+    // The whole warp runs the loop (warp-uniform control flow keeps addresses and descriptors in uniform
+    // registers); one elected lane issues.
+    int s = 0, ph = 1;
+    for (int it = 0; it < n1 + n2; ++it) {
+      mbar_wait(kempty(s), ph);
+      if (elect_one()) {
         mbar_expect_tx(kfull(s), kTileBytes);
+        KVC_TILE_STAMP(true, it, 0);
         const int key0 = tile_of(it) * kTile;
         tma_load_4d(k_s + s * kTileBytes, &tmap_k, kfull(s), 0, key0, kvh, b);
         tma_load_4d(k_s + s * kTileBytes + kHalfBytes, &tmap_k, kfull(s), 64, key0, kvh, b);
+        KVC_STAMP(it == n1 - 1, 12);       // last pass-1 tile requested
+        KVC_STAMP(it == n1 + n2 - 1, 13);  // last pass-2 tile requested
       }
+      __syncwarp();
+      if (++s == S) { s = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
     // ===== MMA issuer: pass 1 D = Q.K^T (lanes = query rows), pass 2 D = K.Q^T (lanes = keys) =====
-    if (lane == 0) {
-      const int fmt = T::kDtype == KVC_BF16 ? 1 : 0;
-      const uint32_t idesc1 = instr_desc(fmt, 128, 128), idesc2 = instr_desc(fmt, 128, nq);
-      mbar_wait(qbar, 0);
-      tc_fence_after();
-      for (int it = 0; it < n1 + n2; ++it) {
-        const int s = it % S;
-        const bool second = it >= n1;
-        mbar_wait(kfull(s), (it / S) & 1);
-        tc_fence_after();
+    // Warp-uniform loop, elected lane issues: with the loop inside `if (lane == 0)` every descriptor
+    // went through R2UR and one tile took ~950 cycles to issue (more than its 512 tensor-pipe cycles).
+    const int fmt = T::kDtype == KVC_BF16 ? 1 : 0;
+    const uint32_t idesc1 = instr_desc(fmt, 128, 128), idesc2 = instr_desc(fmt, 128, nq);
+    mbar_wait(qbar, 0);
+    tc_fence_after();
+    int s = 0, ph = 0, buf = 0, bph = 1;
+    for (int it = 0; it < n1 + n2; ++it) {
+      const bool second = it >= n1;
+      const uint32_t idesc = second ? idesc2 : idesc1;
 #pragma unroll
-        for (int rb = 0; rb < RB; ++rb) {
-          const int j = it * RB + rb, buf = j % kNumBuf;
-          mbar_wait(tempty(buf), ((j / kNumBuf) & 1) ^ 1);
-          tc_fence_after();
-          const uint32_t ks = k_s + s * kTileBytes, qs = q_s + rb * kTileBytes;
+      for (int rb = 0; rb < RB; ++rb) {
+        mbar_wait(tempty(buf), bph);
+        if (rb == 0) mbar_wait(kfull(s), ph);
+        tc_fence_after();
+        KVC_TILE_STAMP(lane == 0, it, 2);
+        const uint64_t kd0 = smem_desc(k_s + s * kTileBytes), qd0 = smem_desc(q_s + rb * kTileBytes);
+        const uint64_t ad0 = second ? kd0 : qd0, bd0 = second ? qd0 : kd0;
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < kD / 16; ++k) {
-            const uint32_t off = (k >> 2) * kHalfBytes + (k & 3) * 32;
-            const uint64_t kd = smem_desc(ks + off), qd = smem_desc(qs + off);
-            tc_mma(tmem_base + buf * 128, second ? kd : qd, second ? qd : kd, second ? idesc2 : idesc1, k > 0);
+            const uint64_t off = (uint64_t)(((k >> 2) * kHalfBytes + (k & 3) * 32) >> 4);  // start-address field is in 16-byte units
+            tc_mma(tmem_base + buf * 128, ad0 + off, bd0 + off, idesc, k > 0);
           }
           tc_commit(tfull(buf));
+          if (rb == RB - 1) tc_commit(kempty(s));
         }
-        tc_commit(kempty(s));
+        __syncwarp();
+        KVC_TILE_STAMP(lane == 0, it, 3);
+        if (++buf == kNumBuf) { buf = 0; bph ^= 1; }
       }
+      if (++s == S) { s = 0; ph ^= 1; }
     }
   } else {
     // ===== epilogue warps =====
@@ -261,8 +330,9 @@ window_score_fused_kernel(const __grid_constant__ CUtensorMap tmap_k, const Para
     const int wg = (warp - 2) >> 2;
     const int quad = warp & 3;
     const int r_loc = quad * 32 + lane;
-    const float2 l2e2 = make_float2(kLog2e, kLog2e);
-
+    float scale = p.scale;
+    unsigned my_gen = 0;
+    if (et == 0) asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(my_gen) : "l"(&g_bar_gen) : "memory");
     // stage the Q block(s): canonical K-major SWIZZLE_128B layout, all chunks in flight
 #pragma unroll
     for (int it = 0; it < (RB * 128 * 16 + kEpiThreads - 1) / kEpiThreads; ++it) {
@@ -282,50 +352,49 @@ window_score_fused_kernel(const __grid_constant__ CUtensorMap tmap_k, const Para
     asm volatile("cp.async.wait_all;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     mbar_arrive(qbar);
+    KVC_STAMP(et == 0, 1);
 
     // ---------------- pass 1: thread <-> query row, columns are keys ----------------
-    float m_run[RB], z_run[RB];
+    float m_run[RB];
+    float2 zacc[RB][4];
 #pragma unroll
-    for (int rb = 0; rb < RB; ++rb) { m_run[rb] = -1e30f; z_run[rb] = 0.f; }
-    int j = wg;
-    for (; j < n1 * RB; j += kNumWG) {
+    for (int rb = 0; rb < RB; ++rb) {
+      m_run[rb] = -1e30f;
+#pragma unroll
+      for (int a = 0; a < 4; ++a) zacc[rb][a] = make_float2(0.f, 0.f);
+    }
+    // (A software-pipelined variant -- TMEM load of tile j+1 issued before the math of tile j -- was
+    // measured slower: 64 live accumulator registers cost more ILP in the math than the ~250 cycles of
+    // load latency per tile that the other three warps of the scheduler mostly cover anyway.)
+    const uint32_t tcol = tmem_base + ((uint32_t)(quad * 32) << 16) + wg * 32;
+    int j = 0;
+    for (; j < n1 * RB; ++j) {
       const int it = j / RB, rb = j % RB, buf = j % kNumBuf;
-      const int key0 = tile_of(it) * kTile;
+      const int key0 = tile_of(it) * kTile + wg * 32;
       mbar_wait(tfull(buf), (j / kNumBuf) & 1);
       tc_fence_after();
-      uint32_t r2[64];
-      load_round<T>(tmem_base + ((uint32_t)(quad * 32) << 16) + buf * 128, p.scale, r2, tempty(buf), lane);
-      if (key0 + kTile > nscore) {  // tile touches the w x w causal block or the ragged end
+      KVC_TILE_STAMP(et == 0, j, 4);
+      uint32_t v[32];
+      tmem_ld32(tcol + buf * 128, v);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty(buf));
+      KVC_TILE_STAMP(et == 0, j, 5);
+      if (key0 + 32 > nscore) {  // chunk touches the w x w causal block or the ragged end
         const int rg = rb * 128 + r_loc;
-        const int hl = rg / W, wi = rg % W;
-        const int last_key = min(p.L - 1, hl < p.groups ? nscore + wi : p.L - 1);
-#pragma unroll
-        for (int i = 0; i < 64; ++i) {
-          const int key = key0 + 2 * i;
-          if (key > last_key) r2[i] = (r2[i] & 0xffff0000u) | (T::kNegInfPair & 0xffffu);
-          if (key + 1 > last_key) r2[i] = (r2[i] & 0x0000ffffu) | (T::kNegInfPair & 0xffff0000u);
-        }
+        const int last_key = min(p.L - 1, rg / W < p.groups ? nscore + rg % W : p.L - 1);
+        p1_chunk<T, true>(v, scale, m_run[rb], zacc[rb], key0, last_key);
+      } else {
+        p1_chunk<T, false>(v, scale, m_run[rb], zacc[rb], 0, 0);
       }
-      uint32_t pm = r2[0];
+      KVC_TILE_STAMP(et == 0 && zacc[rb][0].x >= 0.f, j, 6);
+    }
+    KVC_STAMP(et == 0, 2);  // pass 1 done
+    float z_run[RB];
 #pragma unroll
-      for (int i = 1; i < 64; ++i) pm = T::max2(pm, r2[i]);
-      const float m_new = fmaxf(m_run[rb], fmaxf(T::lo(pm), T::hi(pm)));
-      const float2 ml2 = make_float2(-m_new * kLog2e, -m_new * kLog2e);
-      float2 zacc[4];
-      zacc[0] = make_float2(z_run[rb] * fast_exp2((m_run[rb] - m_new) * kLog2e), 0.f);
-      zacc[1] = zacc[2] = zacc[3] = make_float2(0.f, 0.f);
-#pragma unroll
-      for (int bt = 0; bt < 4; ++bt) {
-        float2 a[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) a[i] = __ffma2_rn(make_float2(T::lo(r2[bt * 16 + i]), T::hi(r2[bt * 16 + i])), l2e2, ml2);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) a[i] = make_float2(fast_exp2(a[i].x), fast_exp2(a[i].y));
-#pragma unroll
-        for (int i = 0; i < 16; ++i) zacc[i & 3] = __fadd2_rn(zacc[i & 3], a[i]);
-      }
-      float2 z2 = __fadd2_rn(__fadd2_rn(zacc[0], zacc[1]), __fadd2_rn(zacc[2], zacc[3]));
-      m_run[rb] = m_new;
+    for (int rb = 0; rb < RB; ++rb) {
+      const float2 z2 = __fadd2_rn(__fadd2_rn(zacc[rb][0], zacc[rb][1]), __fadd2_rn(zacc[rb][2], zacc[rb][3]));
       z_run[rb] = z2.x + z2.y;
     }
 
@@ -347,22 +416,32 @@ window_score_fused_kernel(const __grid_constant__ CUtensorMap tmap_k, const Para
     }
     __threadfence();
     epi_sync();
+    KVC_STAMP(et == 0, 5);  // partials published
     if (et == 0) {
+      // sense-reversing grid barrier on library-owned words: the last CTA to arrive resets the count
+      // and bumps the generation, so no memset node is needed between launches
       const unsigned total = gridDim.x * gridDim.y;
-      atomicAdd(p.sync_count, 1u);
-      unsigned seen = 0;
-      for (unsigned spin = 0; seen < total; ++spin) {
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.sync_count) : "memory");
-        if (seen < total) {
-          __nanosleep(64);
-          if (spin > (1u << 24)) {
-            printf("kvc scores_fused: grid barrier timed out (block %d,%d: %u of %u arrived)\n", blockIdx.x, blockIdx.y, seen, total);
-            __trap();
+      const unsigned old = atomicAdd(&g_bar_count, 1u);
+      if (old == total - 1) {
+        g_bar_count = 0u;
+        __threadfence();
+        atomicAdd(&g_bar_gen, 1u);
+      } else {
+        unsigned gen = my_gen;
+        for (unsigned spin = 0; gen == my_gen; ++spin) {
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(gen) : "l"(&g_bar_gen) : "memory");
+          if (gen == my_gen) {
+            __nanosleep(32);
+            if (spin > (1u << 24)) {
+              printf("kvc scores_fused: grid barrier timed out (block %d,%d)\n", blockIdx.x, blockIdx.y);
+              __trap();
+            }
           }
         }
       }
     }
     epi_sync();
+    KVC_STAMP(et == 0, 6);  // grid barrier passed
     for (int r = et; r < RB * 128; r += kEpiThreads) {
       const float2* st = p.stats + (int64_t)unit * p.nchunks * (RB * 128) + r;
       float M = -1e30f, Z = 0.f;
@@ -388,45 +467,30 @@ window_score_fused_kernel(const __grid_constant__ CUtensorMap tmap_k, const Para
     }
     epi_sync();
 
+    KVC_STAMP(et == 0, 7);  // c_row ready
     // ---------------- pass 2: thread <-> key, columns are the stacked query rows ----------------
-    constexpr int kHeadsPerBlk = 128 / W;
-    for (; j < (n1 + n2) * RB; j += kNumWG) {
+    constexpr int kHeadsPerChunk = 32 / W;
+    for (; j < (n1 + n2) * RB; ++j) {
       const int it = j / RB, rb = j % RB, buf = j % kNumBuf;
-      const int key0 = tile_of(it) * kTile;
+      const int key = tile_of(it) * kTile + r_loc;
       mbar_wait(tfull(buf), (j / kNumBuf) & 1);
       tc_fence_after();
-      uint32_t r2[64];
-      load_round<T>(tmem_base + ((uint32_t)(quad * 32) << 16) + buf * 128, p.scale, r2, tempty(buf), lane);
-      float2 acc[kHeadsPerBlk];
+      KVC_TILE_STAMP(et == 0, j, 4);
+      uint32_t v[32];
+      tmem_ld32(tcol + buf * 128, v);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty(buf));
+      KVC_TILE_STAMP(et == 0, j, 5);
+      float2 acc[kHeadsPerChunk];
 #pragma unroll
-      for (int h = 0; h < kHeadsPerBlk; ++h) acc[h] = make_float2(0.f, 0.f);
-      const float* cr = crow + rb * 128;
-#pragma unroll
-      for (int cc = 0; cc < 4; ++cc) {
-        float2 a[16];
-#pragma unroll
-        for (int q4 = 0; q4 < 8; ++q4) {
-          const float4 c4 = *reinterpret_cast<const float4*>(cr + cc * 32 + q4 * 4);
-          a[2 * q4] = __ffma2_rn(make_float2(T::lo(r2[cc * 16 + 2 * q4]), T::hi(r2[cc * 16 + 2 * q4])), l2e2,
-                                 make_float2(c4.x, c4.y));
-          a[2 * q4 + 1] = __ffma2_rn(make_float2(T::lo(r2[cc * 16 + 2 * q4 + 1]), T::hi(r2[cc * 16 + 2 * q4 + 1])), l2e2,
-                                     make_float2(c4.z, c4.w));
-        }
-        uint32_t pp[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) pp[i] = T::pack(fast_exp2(a[i].x), fast_exp2(a[i].y));
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int col = cc * 32 + 2 * i;
-          acc[col / W] = __fadd2_rn(acc[col / W], make_float2(T::lo(pp[i]), T::hi(pp[i])));
-        }
-      }
-#pragma unroll
-      const int key = key0 + r_loc;
+      for (int h = 0; h < kHeadsPerChunk; ++h) acc[h] = make_float2(0.f, 0.f);
+      p2_chunk<T, W>(v, scale, crow + rb * 128 + wg * 32, acc);
       if (key < nscore) {
 #pragma unroll
-        for (int h = 0; h < kHeadsPerBlk; ++h) {
-          const int head = rb * kHeadsPerBlk + h;
+        for (int h = 0; h < kHeadsPerChunk; ++h) {
+          const int head = (rb * 128 + wg * 32) / W + h;
           if (head < p.groups) {
             float s = acc[h].x + acc[h].y;
             if (p.reduce_mean) s = s / (float)p.w;
@@ -434,11 +498,21 @@ window_score_fused_kernel(const __grid_constant__ CUtensorMap tmap_k, const Para
           }
         }
       }
+      KVC_TILE_STAMP(et == 0 && acc[0].x >= 0.f, j, 6);
     }
   }
 
+  KVC_STAMP(tid == 64, 8);  // pass 2 done
   tc_fence_before();
   __syncthreads();
+  KVC_STAMP(tid == 0, 11);
+#ifdef KVC_TRACE
+  {
+    const int cta = blockIdx.y * gridDim.x + blockIdx.x;
+    const int c = cta == 0 ? 0 : cta == 1 ? 1 : cta == 70 ? 2 : cta == 143 ? 3 : -1;
+    if (c >= 0) for (int i = tid; i < 64 * 8; i += kThreads) g_tile_trace[c][i / 8][i % 8] = s_tile_trace[i / 8][i % 8];
+  }
+#endif
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -484,7 +558,6 @@ static int launch(const CUtensorMap& tmap, const Params& sp, int units, cudaStre
   auto kern = window_score_fused_kernel<T, RB, W>;
   const int smem = Smem<RB>::kAlloc;
   KVC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  KVC_CUDA_TRY(cudaMemsetAsync(sp.sync_count, 0, sizeof(unsigned), stream));
   // cooperative launch: the grid is scheduled only when every CTA can be resident, so two grids
   // with barriers (other streams / processes) can never hold each other's SMs hostage
   cudaLaunchConfig_t cfg{};
@@ -510,18 +583,27 @@ static int dispatch_w(const CUtensorMap& tmap, const Params& sp, int units, cuda
   switch (sp.w) {
     case 8: return launch<T, RB, 8>(tmap, sp, units, stream);
     case 16: return launch<T, RB, 16>(tmap, sp, units, stream);
-    case 32: return launch<T, RB, 32>(tmap, sp, units, stream);
-    default: return launch<T, RB, 64>(tmap, sp, units, stream);
+    default: return launch<T, RB, 32>(tmap, sp, units, stream);
   }
 }
 
 }  // namespace tcf
+
+#ifdef KVC_TRACE
+extern "C" int kvc_debug_ftrace(long long* out, int n) {
+  return (int)cudaMemcpyFromSymbol(out, tcf::g_trace, sizeof(long long) * (size_t)n);
+}
+extern "C" int kvc_debug_tile_trace(unsigned* out) {
+  return (int)cudaMemcpyFromSymbol(out, tcf::g_tile_trace, sizeof(unsigned) * 4 * 64 * 8);
+}
+#endif
 
 bool window_scores_tc_supported(int B, int Hq, int Hkv, int L, int d, int w);
 
 // The grid barrier needs every CTA resident at once: units * chunks must fit the SM count.
 bool window_scores_fused_supported(int B, int Hq, int Hkv, int L, int d, int w) {
   if (!window_scores_tc_supported(B, Hq, Hkv, L, d, w)) return false;
+  if (w > 32) return false;  // a 64-row head spans two warpgroups' columns: the two-launch kernel covers it
   const tcf::Plan pl = tcf::make_plan(B, Hq, Hkv, L, w);
   return B * Hkv * pl.nchunks <= sm_count();
 }
@@ -566,7 +648,6 @@ int window_scores_fused(const void* q, int64_t q_sb, int64_t q_sh, int64_t q_sl,
   sp.scale = 1.0f / sqrtf((float)d);
   sp.reduce_mean = reduce == KVC_REDUCE_MEAN;
   sp.stats = (float2*)workspace;
-  sp.sync_count = (unsigned*)((char*)workspace + pl.stats_bytes);
   sp.out = (uint16_t*)out_scores;
   const int units = B * Hkv;
   if (dtype == KVC_BF16)
