@@ -314,14 +314,16 @@ def run_ours(args, wl):
 
     def time_graph(g_, reps):
         g_.replay()
-        torch.cuda.synchronize()
-        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
+        barrier()  # ranks time the same phase at the same time (no neighbour's host copies in the bracket)
+        ts = []
         for _ in range(reps):
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
             g_.replay()
-        b_.record()
-        torch.cuda.synchronize()
-        return a.elapsed_time(b_) / reps
+            b_.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b_))
+        return statistics.median(ts)
 
     keeps = [kept_rows(wl, l) - w for l in range(nl)]
     g_sc, scs = phase_graph(lambda: [_native.window_scores(Qs[l], Ks[l], w, "sum", impl) for l in range(nl)])
@@ -345,9 +347,18 @@ def run_ours(args, wl):
     dom_bytes_per_launch = alg[dominant] / nl if dominant != "select" else (sb + gb) / nl
     dom_ms = tot[dominant] / nl
     achieved = dom_bytes_per_launch / (dom_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": {"scores": "window_scores (stats+scores passes)", "select": "pool_topk",
-                                           "gather": "gather_rows"}[dominant],
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    # DRAM traffic per launch of the dominant kernel from the committed ncu --set full capture
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1b_traffic.json")))
+        kname = {"scores": "window_score_fused_kernel", "select": "topk_cluster_kernel", "gather": "gather_rows_kernel"}
+        if args.workload == "pyramidkv_llama3_8b_32k":
+            traffic = tj["dram_bytes_per_launch"].get(kname[dominant])
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": {"scores": "window_scores (fused stats+scores passes, one launch)",
+                                           "select": "pool_topk", "gather": "gather_rows"}[dominant],
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "bytes_per_launch": dom_bytes_per_launch, "ms_per_launch": dom_ms,
                 "phase_ms_per_step": tot,
                 "step_frac_of_hbm_roofline": (sb + gb) / (ms_per_step * 1e-3) / 1e9 / peak}

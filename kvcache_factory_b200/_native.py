@@ -209,8 +209,19 @@ def pool_topk(scores: torch.Tensor, kernel_size: int, pooling, k: int, k_per_row
 
 def gather_dense(key_states: torch.Tensor, value_states: torch.Tensor, idx, num_heads: int, n_sel: int,
                  window_size: int):
-    """Compressed (K', V') [B,Hq,n_sel+w,d]; ``idx=None`` keeps the first n_sel rows (StreamingLLM)."""
-    dev = _require_cuda(key_states, value_states)
+    """Compressed (K', V') [B,Hq,n_sel+w,d]; ``idx=None`` keeps the first n_sel rows (StreamingLLM).
+
+    ``value_states`` may instead be a PINNED host tensor (same shape/dtype): V is only ever read at the
+    selected rows, so a caller holding its KV in host memory does not have to move the other rows to
+    the device -- the kernel's 16-byte loads then read the selected rows straight over PCIe through
+    the unified address space (pinned allocations are device-accessible at their host address).
+    """
+    if value_states.device.type == "cpu":
+        if not value_states.is_pinned():
+            raise RuntimeError("a host value_states tensor must be pinned (page-locked) memory")
+        dev = _require_cuda(key_states)
+    else:
+        dev = _require_cuda(key_states, value_states)
     B, Hkv, L, d = key_states.shape
     if value_states.shape != key_states.shape or value_states.dtype != key_states.dtype:
         raise ValueError("key_states and value_states must have the same shape and dtype")

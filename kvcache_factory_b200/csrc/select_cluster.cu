@@ -19,6 +19,13 @@
 namespace kvc {
 namespace cl {
 
+#ifdef KVC_TRACE
+__device__ long long g_sel_trace[16];
+#define SEL_STAMP(slot) do { if (blockIdx.y == 0 && blockIdx.x == 0 && threadIdx.x == 0) g_sel_trace[slot] = clock64(); } while (0)
+#else
+#define SEL_STAMP(slot) do { } while (0)
+#endif
+
 constexpr int kThreads = 1024;
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxK = 8192;
@@ -159,6 +166,7 @@ topk_cluster_kernel(const uint16_t* __restrict__ scores, int n, int kernel_size,
   const int radius = POOL == KVC_POOL_NONE ? 0 : kernel_size / 2;
   const int s0 = (int)crank * SL;
 
+  SEL_STAMP(0);
   // ---- 1. load this thread's E scores (+ pooling halo) straight into registers, pool -------------
   // Own elements: 8-element (16-byte) vector loads when the row allows it -- a warp then reads one
   // contiguous span; the 2*kHalo halo elements are the neighbours' own elements (L1 hits).
@@ -233,6 +241,7 @@ topk_cluster_kernel(const uint16_t* __restrict__ scores, int n, int kernel_size,
       }
     }
   }
+  SEL_STAMP(1);
   const int nvalid = max(0, min(E, n - j0));
   const float sum_all_cta = out_sums ? block_sum_f(part_all, sh.fsum) : 0.f;
   if (k == 0) {  // uniform over the cluster; nothing to select (AdaKV asks only for pooled scores / sums)
@@ -250,6 +259,7 @@ topk_cluster_kernel(const uint16_t* __restrict__ scores, int n, int kernel_size,
     return;
   }
 
+  SEL_STAMP(2);
   // ---- 2a. key range of the row ---------------------------------------------------------------------
   int kmin = 0xffff, kmax = 0;
 #pragma unroll
@@ -273,6 +283,7 @@ topk_cluster_kernel(const uint16_t* __restrict__ scores, int n, int kernel_size,
   const int range = kmax - kmin;
   const int sh1 = range < 256 ? 0 : (32 - __clz(range)) - 8;  // bins of 2^sh1 keys, <= 256 bins
 
+  SEL_STAMP(3);
   // ---- 2b. counting rounds -----------------------------------------------------------------------------
   int krem = k, thr_key;
   {
@@ -296,6 +307,7 @@ topk_cluster_kernel(const uint16_t* __restrict__ scores, int n, int kernel_size,
       thr_key += b2v;
     }
   }
+  SEL_STAMP(4);
   const int need_eq = krem, count_gt = k - krem;
 
   // ---- 3. ordered compaction into CTA 0 -----------------------------------------------------------
@@ -308,6 +320,7 @@ topk_cluster_kernel(const uint16_t* __restrict__ scores, int n, int kernel_size,
   int total;
   const int ex = block_scan_excl(gt | (eq << 16), sh.warp_tmp, total);
   if (tid == 0) { sh.totals[0] = total & 0xffff; sh.totals[1] = (int)((uint32_t)total >> 16); }
+  SEL_STAMP(5);
   cluster_sync();  // totals visible; also: every CTA is past its last read of `stage`, so CTA 0's buffers are free
   int gbase = 0, ebase = 0;
   for (uint32_t c = 0; c < crank; ++c) {
@@ -336,6 +349,7 @@ topk_cluster_kernel(const uint16_t* __restrict__ scores, int n, int kernel_size,
   }
   cluster_sync();  // all winners (and partial sums) have landed in / are readable by CTA 0
 
+  SEL_STAMP(6);
   // ---- 4. CTA 0: stable LSD radix sort by descending key, emit -------------------------------------
   if (crank == 0) {
     if (out_sums && tid == 0) {
@@ -392,8 +406,10 @@ topk_cluster_kernel(const uint16_t* __restrict__ scores, int n, int kernel_size,
       __syncthreads();
       cur ^= 1;
     }
+    SEL_STAMP(7);
     for (int r = tid; r < k; r += kThreads) out_idx[(int64_t)row * idx_stride + r] = (int32_t)sidx[cur][r];
   }
+  SEL_STAMP(8);
   cluster_sync();  // keep every CTA's shared memory alive until CTA 0 has read the partial sums
 }
 
@@ -443,6 +459,10 @@ static int dispatch_pool(int pool, const void* scores, int rows, int n, int kern
 }
 
 }  // namespace cl
+
+#ifdef KVC_TRACE
+extern "C" int kvc_debug_sel_trace(long long* out) { return (int)cudaMemcpyFromSymbol(out, cl::g_sel_trace, sizeof(long long) * 16); }
+#endif
 
 // Returns 1 when the shape is outside what the cluster kernel covers (caller falls back).
 int pool_topk_cluster(const void* scores, int rows, int n, int dtype, int kernel_size, int pool, int k,

@@ -2,10 +2,12 @@
 
 This is the call a caller without device-resident tensors makes (offloaded prefill, a remote
 prefill worker handing KV over host memory, the ``e2e`` leg of ``bench.py``).  Per layer it copies
-K, V and the last ``window_size`` query rows to the device (the only query rows the window-scored
+K and the last ``window_size`` query rows to the device (the only query rows the window-scored
 policies read, reference ``pyramidkv_utils.py:317``), runs the cluster's CUDA path, and copies the
-compressed rows back.  Copies run on their own streams with double-buffered staging so that layer
-l+1's host->device transfer and layer l-1's device->host transfer overlap layer l's kernels.
+compressed rows back.  V never moves as a whole: the path reads V only at the selected rows, so the
+gather kernel loads those rows directly from the pinned host buffer (``zero_copy_v``; 4x fewer V
+bytes over PCIe at cfg-2).  Copies run on their own streams with double-buffered staging so that
+layer l+1's host->device transfer and layer l-1's device->host transfer overlap layer l's kernels.
 """
 from __future__ import annotations
 
@@ -15,7 +17,8 @@ import torch
 
 
 class HostCompressor:
-    def __init__(self, clusters: Sequence, num_key_value_groups: int, device: torch.device):
+    def __init__(self, clusters: Sequence, num_key_value_groups: int, device: torch.device, zero_copy_v: bool = True):
+        self.zero_copy_v = zero_copy_v
         self.clusters = list(clusters)
         self.groups = num_key_value_groups
         self.device = device
@@ -53,12 +56,18 @@ class HostCompressor:
                 if l >= 2:
                     self.s_in.wait_event(ev_done[l - 2])           # staging set is free again
                 dk.copy_(host_k[l], non_blocking=True)
-                dv.copy_(host_v[l], non_blocking=True)
+                if not self.zero_copy_v:
+                    dv.copy_(host_v[l], non_blocking=True)
                 dq.copy_(host_q_window[l], non_blocking=True)
                 ev_in[l].record(self.s_in)
-            h2d += host_k[l].numel() * host_k[l].element_size() * 2 + host_q_window[l].numel() * dq.element_size()
             cur.wait_event(ev_in[l])
-            kc, vc = self.clusters[l].update_kv_window(dk, dq, dv, self.groups, seq_len)
+            kc, vc = self.clusters[l].update_kv_window(dk, dq, host_v[l] if self.zero_copy_v else dv, self.groups,
+                                                       seq_len)
+            esz = host_k[l].element_size()
+            # bytes that cross PCIe towards the device: all of K, the query window, and either all of V or
+            # only the V rows the gather kernel reads
+            h2d += host_k[l].numel() * esz + host_q_window[l].numel() * esz
+            h2d += vc.numel() * esz if self.zero_copy_v and vc is not host_v[l] else host_v[l].numel() * esz
             ev_done[l].record(cur)
             if self._out[l] is None or self._out[l][0].shape != kc.shape:
                 self._out[l] = (torch.empty(kc.shape, dtype=kc.dtype, pin_memory=True),

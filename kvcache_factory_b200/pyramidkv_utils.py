@@ -164,7 +164,8 @@ class _ScoredCluster:
                 out = N.gather_dense(key_states, value_states, idx, Hq, n_keep, w)
             if not torch.cuda.is_current_stream_capturing():
                 for t in (scores, key_states, value_states):
-                    t.record_stream(side)
+                    if t.is_cuda:
+                        t.record_stream(side)
             self._inflight = (scores, idx)
             if self.keep_debug:
                 self.debug = dict(scores=scores, pooled=pooled, indices=idx, n_keep=n_keep)

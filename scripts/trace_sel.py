@@ -1,13 +1,15 @@
+"""Phase timeline of the cluster select kernel (library built with `make TRACE=1`)."""
 import os, sys, ctypes
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from kvcache_factory_b200 import _native
 dev = torch.device("cuda:0")
-s = (torch.rand(32, 32736, device=dev) ** 4).to(torch.bfloat16)
+sc = (torch.rand(1, 32, 32736, device=dev) * 1e-3).to(torch.bfloat16)
 for _ in range(3):
-    idx, _, _ = _native.pool_topk(s, 7, "avgpool", 3932)
+    idx = _native.pool_topk(sc, 7, "avgpool", 2016)[0]
 torch.cuda.synchronize()
-raw = ctypes.CDLL(_native.LIB_PATH); buf = (ctypes.c_longlong * 64)(); raw.kvc_debug_seltrace(buf)
-t = list(buf); names = ["start", "pooled", "minmax xchg done", "round1 counted", "r1 cluster sync", "round2 counted", "r2 cluster sync", "threshold known", "local scan done", "totals sync", "scatter done", "scatter sync", "sort+emit done (cta0)", "final sync"]
-for i, nm in enumerate(names):
-    print(f"{nm:26s} {t[i]-t[0]:8d}  (+{t[i]-t[i-1] if i else 0})")
+raw = ctypes.CDLL(_native.LIB_PATH); buf = (ctypes.c_longlong * 16)(); raw.kvc_debug_sel_trace(buf)
+t = list(buf)
+names = ["start", "loaded+pooled", "sums done", "minmax done", "thresholds done", "scan done", "compacted", "sorted", "written"]
+for i in range(1, 9):
+    print(f"{names[i]:16s} +{t[i] - t[i-1]:7d} cycles  (t={t[i] - t[0]})")

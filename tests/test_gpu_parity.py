@@ -72,6 +72,47 @@ def test_gather_dense_bit_exact(layout, dtype):
     assert torch.equal(out_k.cpu(), ref_k) and torch.equal(out_v.cpu(), ref_v)
 
 
+def test_gather_reads_value_rows_from_pinned_host_memory():
+    """V is only read at the selected rows: a pinned host V gives the same bits as a device V."""
+    shape = Shape(B=1, Hq=8, Hkv=2, L=1500, d=128)
+    w, n_sel = 32, 300
+    g = torch.Generator().manual_seed(11)
+    _, K, V = make_qkv(shape, torch.bfloat16, layer_idx=1, window=w)
+    idx = torch.stack([torch.randperm(shape.L - w, generator=g)[:n_sel] for _ in range(shape.Hq)]).view(1, shape.Hq, n_sel)
+    ref_k, ref_v = O.gather_and_append_window(O.repeat_kv(K, 4), O.repeat_kv(V, 4), idx, w)
+    out_k, out_v = _native.gather_dense(K.to(dev()), V.pin_memory(), idx.to(dev(), torch.int32).contiguous(),
+                                        shape.Hq, n_sel, w)
+    assert out_v.is_cuda and torch.equal(out_k.cpu(), ref_k) and torch.equal(out_v.cpu(), ref_v)
+    with pytest.raises(RuntimeError, match="pinned"):
+        _native.gather_dense(K.to(dev()), V, idx.to(dev(), torch.int32).contiguous(), shape.Hq, n_sel, w)
+
+
+@pytest.mark.parametrize("zero_copy_v", [True, False])
+def test_host_compressor_matches_device_path(zero_copy_v):
+    """Host-buffer entry (pinned K/V/Q-window in, K'/V' out) == the device-resident update_kv, bit for bit."""
+    from kvcache_factory_b200.host_api import HostCompressor
+    shape = Shape(1, 8, 2, 2048, 128)
+    w, cap, nl = 32, 256, 3
+    mk = lambda l: SnapKVCluster(w, cap, 7, "avgpool")
+    dev_cl, host_cl = [mk(l) for l in range(nl)], [mk(l) for l in range(nl)]
+    hK, hV, hQ, ref = [], [], [], []
+    for l in range(nl):
+        Q, K, V = make_qkv(shape, torch.bfloat16, layer_idx=l, dist="peaked", window=w, q_window_only=True)
+        Kc, Vc = dev_cl[l].update_kv(K.to(dev()), Q.to(dev()), V.to(dev()), None, 4)
+        ref.append((Kc.cpu(), Vc.cpu()))
+        hK.append(K.pin_memory()); hV.append(V.pin_memory()); hQ.append(Q[:, :, -w:].contiguous().pin_memory())
+    hc = HostCompressor(host_cl, 4, dev(), zero_copy_v=zero_copy_v)
+    out = hc.run(hK, hQ, hV, shape.L)
+    torch.cuda.synchronize()
+    for l in range(nl):
+        assert torch.equal(out[l][0], ref[l][0]) and torch.equal(out[l][1], ref[l][1])
+    kept = nl * shape.B * shape.Hq * cap * shape.d * 2
+    full = nl * shape.B * shape.Hkv * shape.L * shape.d * 2
+    qb = nl * shape.B * shape.Hq * w * shape.d * 2
+    assert hc.d2h_bytes == 2 * kept
+    assert hc.h2d_bytes == full + qb + (kept if zero_copy_v else full)
+
+
 @pytest.mark.parametrize("name", golden_cases("streamingllm") + ["snapkv_passthrough"])
 def test_streamingllm_and_passthrough_match_reference_vectors(name):
     c, z, (Q, K, V) = load_golden(name)
