@@ -269,6 +269,12 @@ window_score_fused_kernel(const __grid_constant__ CUtensorMap tmap_k, const Para
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation) may overlap the tail
+  // of the previous kernel in the stream; nothing below may start before that kernel has completed and
+  // its writes are visible (inputs, the statistics workspace, the grid-barrier words).  Letting our own
+  // dependents launch right away is safe for the same reason: they wait for our completion in turn.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp == 0) {
     // ===== TMA producer: one stream of n1 + n2 tiles =====
@@ -363,9 +369,9 @@ window_score_fused_kernel(const __grid_constant__ CUtensorMap tmap_k, const Para
 #pragma unroll
       for (int a = 0; a < 4; ++a) zacc[rb][a] = make_float2(0.f, 0.f);
     }
-    // (A software-pipelined variant -- TMEM load of tile j+1 issued before the math of tile j -- was
-    // measured slower: 64 live accumulator registers cost more ILP in the math than the ~250 cycles of
-    // load latency per tile that the other three warps of the scheduler mostly cover anyway.)
+    // (Two software-pipelined variants were measured slower, 36.9 / 42 us vs 34.4 us per launch: the TMEM
+    // load of tile j+1 issued before the math of tile j into a second register buffer, and issued
+    // between the convert and exp halves of tile j into the registers the convert half had just freed.)
     const uint32_t tcol = tmem_base + ((uint32_t)(quad * 32) << 16) + wg * 32;
     int j = 0;
     for (; j < n1 * RB; ++j) {
@@ -565,15 +571,19 @@ static int launch(const CUtensorMap& tmap, const Params& sp, int units, cudaStre
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeCooperative;
-  attr[0].val.cooperative = 1;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  attr[1].id = cudaLaunchAttributeCooperative;
+  attr[1].val.cooperative = 1;
   cfg.attrs = attr;
   // KVC_FUSED_COOP=0: plain launch.  CTAs then trickle onto SMs as other streams' kernels (e.g. the
   // asynchronous select/gather tail) retire instead of waiting for a fully free GPU; only safe when
   // no second barrier-synchronised grid can run concurrently on the device.
   static const bool coop = [] { const char* e = getenv("KVC_FUSED_COOP"); return !(e && e[0] == '0'); }();
-  cfg.numAttrs = coop ? 1 : 0;
+  static const bool pdl = [] { const char* e = getenv("KVC_PDL"); return !(e && e[0] == '0'); }();
+  // the cooperative attribute and programmatic serialization do not combine: PDL only on plain launches
+  if (coop) { attr[0] = attr[1]; cfg.numAttrs = 1; } else { cfg.numAttrs = pdl ? 1 : 0; }
   KVC_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, tmap, sp));
   return launch_status("window_score_fused_kernel");
 }
