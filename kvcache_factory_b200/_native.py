@@ -179,8 +179,21 @@ def h2o_scores(query_states: torch.Tensor, key_states: torch.Tensor, window_size
 
 
 def pool_topk(scores: torch.Tensor, kernel_size: int, pooling, k: int, k_per_row: torch.Tensor = None,
-              want_pooled: bool = False, want_sums: bool = False):
-    """Pool + per-row top-k.  Returns (idx int32 [..., k], pooled or None, sums float[rows,2] or None)."""
+              want_pooled: bool = False, want_sums: bool = False, sums_only: bool = False):
+    """Pool + per-row top-k.  Returns (idx int32 [..., k], pooled or None, sums float[rows,2] or None).
+
+    ``sums_only``: only the pooled scores and the (top-k, all) sums are wanted; no indices are produced
+    (idx is returned as None) and the kernel stops after the threshold search."""
+    if sums_only:
+        try:
+            return _pool_topk(scores, kernel_size, pooling, k, k_per_row, want_pooled, True, no_idx=True)
+        except KvcError as e:
+            if e.status != -2:
+                raise
+    return _pool_topk(scores, kernel_size, pooling, k, k_per_row, want_pooled, want_sums or sums_only)
+
+
+def _pool_topk(scores, kernel_size, pooling, k, k_per_row, want_pooled, want_sums, no_idx=False):
     dev = _require_cuda(scores)
     code = dtype_code(scores.dtype)
     pcode = pool_code(pooling)
@@ -189,7 +202,7 @@ def pool_topk(scores: torch.Tensor, kernel_size: int, pooling, k: int, k_per_row
     for s in lead:
         rows *= s
     scores = scores.contiguous()
-    idx = torch.empty((*lead, k), dtype=torch.int32, device=dev)
+    idx = None if no_idx else torch.empty((*lead, k), dtype=torch.int32, device=dev)
     pooled = torch.empty_like(scores) if want_pooled else None
     sums = torch.empty((rows, 2), dtype=torch.float32, device=dev) if want_sums else None
     if k_per_row is not None:
@@ -201,7 +214,7 @@ def pool_topk(scores: torch.Tensor, kernel_size: int, pooling, k: int, k_per_row
         ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=dev)
         _check("kvc_pool_topk", lib().kvc_pool_topk(
             scores.data_ptr(), rows, n, code, kernel_size, pcode, k,
-            k_per_row.data_ptr() if k_per_row is not None else None, idx.data_ptr(), k,
+            k_per_row.data_ptr() if k_per_row is not None else None, idx.data_ptr() if idx is not None else None, k,
             pooled.data_ptr() if pooled is not None else None, sums.data_ptr() if sums is not None else None,
             ws.data_ptr(), ws.numel(), _stream(dev)))
     return idx, pooled, sums

@@ -159,7 +159,7 @@ int kvc_pool_topk(const void* scores, int rows, int n, int dtype, int kernel_siz
                   const int32_t* k_per_row, int32_t* out_idx, int64_t idx_stride, void* out_pooled, float* out_sums,
                   void* workspace, size_t workspace_bytes, void* stream) {
   if (int rc = check_device()) return rc;
-  KVC_REQUIRE(scores && workspace && (out_idx || k == 0), KVC_ERR_ARG, "null pointer argument");
+  KVC_REQUIRE(scores && workspace && (out_idx || k == 0 || out_sums), KVC_ERR_ARG, "null pointer argument");
   KVC_REQUIRE(rows > 0 && n > 0, KVC_ERR_ARG, "rows=%d n=%d must be positive", rows, n);
   KVC_REQUIRE(k >= 0 && k <= n, KVC_ERR_ARG, "k=%d outside [0, n=%d] (torch.topk raises for k > n)", k, n);
   KVC_REQUIRE(idx_stride >= k, KVC_ERR_ARG, "idx_stride %lld < k %d", (long long)idx_stride, k);

@@ -264,6 +264,9 @@ int pool_topk(const void* scores, int rows, int n, int dtype, int kernel_size, i
                                      out_pooled, out_sums, stream);
     if (rc != 1) return rc;  // 1 = shape outside the cluster kernel: fall through to the one-CTA-per-row kernel
   }
+  KVC_REQUIRE(out_idx != nullptr || k == 0, KVC_ERR_UNSUPPORTED,
+              "sums-only select (out_idx == NULL with k > 0) is implemented by the cluster kernel only (rows=%d n=%d k=%d)",
+              rows, n, k);
   const int kpad = next_pow2(k > 1 ? k : 1);
   const size_t keys_bytes = ((size_t)rows * n * 2 + 255) & ~(size_t)255;
   uint16_t* keys = (uint16_t*)workspace;

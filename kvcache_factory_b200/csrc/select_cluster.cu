@@ -310,6 +310,31 @@ topk_cluster_kernel(const uint16_t* __restrict__ scores, int n, int kernel_size,
   SEL_STAMP(4);
   const int need_eq = krem, count_gt = k - krem;
 
+  if (out_idx == nullptr) {
+    // Sums only (AdaKV's ratio normalisation, pyramidkv_utils.py:706-711): the sum of the k largest
+    // pooled values follows from the threshold alone -- no compaction, no sort, no index output.
+    float part_top = 0.f;
+#pragma unroll
+    for (int i = 0; i < E; ++i)
+      if (i < nvalid && (int)keys[i] > thr_key) part_top += T::to_float((uint16_t)key_to_float16_bits(keys[i]));
+    const float st = block_sum_f(part_top, sh.fsum);
+    if (tid == 0) { sh.psum[0] = st; sh.psum[1] = sum_all_cta; }
+    cluster_sync();
+    if (crank == 0 && tid == 0 && out_sums) {
+      float a = 0.f, bsum = 0.f;
+      for (uint32_t c = 0; c < csize; ++c) {
+        a += ld_cluster_f32(map_to_rank(&sh.psum[0], c));
+        bsum += ld_cluster_f32(map_to_rank(&sh.psum[1], c));
+      }
+      const float tv = T::to_float((uint16_t)key_to_float16_bits((uint32_t)thr_key));
+      for (int e = 0; e < need_eq; ++e) a += tv;   // the ties taken at the threshold all carry its value
+      out_sums[2 * row] = a;
+      out_sums[2 * row + 1] = bsum;
+    }
+    cluster_sync();
+    return;
+  }
+
   // ---- 3. ordered compaction into CTA 0 -----------------------------------------------------------
   int gt = 0, eq = 0;
 #pragma unroll
@@ -446,7 +471,9 @@ static int dispatch_e(const void* scores, int rows, int n, int kernel_size, int 
   // slice = 1024*E scores per CTA
   if (n <= 4096) return launch<T, 4, POOL>(scores, rows, n, 1, kernel_size, k, k_per_row, out_idx, idx_stride, out_pooled, out_sums, stream);
   if (n <= 16384) return launch<T, 4, POOL>(scores, rows, n, (n + 4095) / 4096, kernel_size, k, k_per_row, out_idx, idx_stride, out_pooled, out_sums, stream);
-  if (n <= 65536) return launch<T, 8, POOL>(scores, rows, n, (n + 8191) / 8192, kernel_size, k, k_per_row, out_idx, idx_stride, out_pooled, out_sums, stream);
+  // one CTA occupies a whole SM (1 024 threads): prefer the slice length that keeps rows * C within one wave
+  if (n <= 32768 || (n <= 65536 && rows * ((n + 8191) / 8192) <= sm_count()))
+    return launch<T, 8, POOL>(scores, rows, n, (n + 8191) / 8192, kernel_size, k, k_per_row, out_idx, idx_stride, out_pooled, out_sums, stream);
   return launch<T, 16, POOL>(scores, rows, n, (n + 16383) / 16384, kernel_size, k, k_per_row, out_idx, idx_stride, out_pooled, out_sums, stream);
 }
 

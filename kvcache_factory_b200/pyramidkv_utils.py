@@ -356,18 +356,17 @@ class AdaKVCluster:
         assert bsz == 1                                              # :724
 
         scores = N.window_scores(query_states, key_states, w, "mean", self.score_impl)
-        idx_base, pooled, sums = N.pool_topk(scores, self.kernel_size, self.pooling, self.base_capacity,
-                                             want_pooled=True, want_sums=True)
+        # pooled scores + the per-head sums of (top-base, all) that the ratio normalisation needs (:706-711);
+        # the capacities come out of the global allocation, then ONE per-head top-cap_h select
+        _, pooled, sums = N.pool_topk(scores, self.kernel_size, self.pooling, self.base_capacity,
+                                      want_pooled=True, want_sums=True, sums_only=True)
         cap, head_lens, cu_klen = N.adakv_allocate(pooled.view(num_heads, n), sums, self.base_capacity,
                                                    self.floor_ratio, bool(self.normalize), w)
         cap_host = cap.cpu()                                         # the reference syncs here too (:718)
         max_cap = int(cap_host.max())
         klen_sum = int(cap_host.sum()) + num_heads * w
-        if max_cap <= self.base_capacity:
-            idx = idx_base.view(num_heads, self.base_capacity)       # prefixes of the sorted top-base list
-        else:
-            idx, _, _ = N.pool_topk(scores, self.kernel_size, self.pooling, max_cap, k_per_row=cap)
-            idx = idx.view(num_heads, max_cap)
+        idx, _, _ = N.pool_topk(scores, self.kernel_size, self.pooling, max_cap, k_per_row=cap)
+        idx = idx.view(num_heads, max_cap)
         flat_k, flat_v = N.gather_varlen(key_states, value_states, idx, cap, cu_klen, num_heads, w, max_cap,
                                          klen_sum)
         self._init_metadata(device, num_heads, head_lens, cu_klen, klen_sum, max_cap + w)
