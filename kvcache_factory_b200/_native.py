@@ -230,9 +230,9 @@ def gather_dense(key_states: torch.Tensor, value_states: torch.Tensor, idx, num_
     the unified address space (pinned allocations are device-accessible at their host address).
     """
     if value_states.device.type == "cpu":
+        dev = _require_cuda(key_states)                              # K is always read on the device
         if not value_states.is_pinned():
             raise RuntimeError("a host value_states tensor must be pinned (page-locked) memory")
-        dev = _require_cuda(key_states)
     else:
         dev = _require_cuda(key_states, value_states)
     B, Hkv, L, d = key_states.shape

@@ -1,6 +1,8 @@
 // extern "C" surface of libkvc_b200.so (declared in include/kvc_b200.h): argument validation,
 // device check, dispatch to the sm_100a kernels.  No torch types cross this boundary.
+#include <algorithm>
 #include <atomic>
+#include <vector>
 
 #include "common.cuh"
 
@@ -38,6 +40,21 @@ int adakv_allocate(const void*, const float*, int, int, int, int, float, int, in
 static std::atomic<unsigned long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 unsigned long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
+
+#ifdef KVC_TRACE
+static unsigned long long* g_tl_dev = nullptr;
+static int g_tl_kind[4096];
+static std::atomic<int> g_tl_next{0};
+unsigned long long* timeline_slot(int kind) {
+  if (!g_tl_dev) {
+    cudaMalloc(&g_tl_dev, 4096 * 16);
+    cudaMemset(g_tl_dev, 0xff, 4096 * 16);
+  }
+  const int i = g_tl_next.fetch_add(1) % 4096;
+  g_tl_kind[i] = kind;
+  return g_tl_dev + 2 * i;
+}
+#endif
 
 static thread_local char g_err[512] = "";
 char* last_error_buffer() { return g_err; }
@@ -91,6 +108,20 @@ static int check_shape(int B, int Hq, int Hkv, int L, int d, int w, int dtype) {
 using namespace kvc;
 
 extern "C" {
+
+#ifdef KVC_TRACE
+// out[3*i] = kind (0 scoring, 1 select, 2 gather), out[3*i+1] = start ns, out[3*i+2] = end ns; returns #entries
+int kvc_debug_timeline(long long* out, int max_entries, int reset) {
+  const int n = std::min(std::min(g_tl_next.load(), 4096), max_entries);
+  if (n > 0 && g_tl_dev) {
+    std::vector<unsigned long long> h(2 * n);
+    cudaMemcpy(h.data(), g_tl_dev, 16 * (size_t)n, cudaMemcpyDeviceToHost);
+    for (int i = 0; i < n; ++i) { out[3 * i] = g_tl_kind[i]; out[3 * i + 1] = (long long)h[2 * i]; out[3 * i + 2] = (long long)~h[2 * i + 1]; }
+  }
+  if (reset && g_tl_dev) { cudaMemset(g_tl_dev, 0xff, 4096 * 16); }
+  return n;
+}
+#endif
 
 int kvc_version(void) { return KVC_ABI_VERSION; }
 const char* kvc_last_error(void) { return last_error_buffer(); }

@@ -128,4 +128,21 @@ __device__ __forceinline__ void st_stream16(void* p, const int4& v) {
 
 constexpr float kLog2e = 1.4426950408889634f;
 
+// ---- developer timeline (`make TRACE=1`): per launch, the earliest CTA start and the latest CTA end in
+// globaltimer ns; kvc_debug_timeline() reads them back.  tl == nullptr in the shipped library.
+#ifdef KVC_TRACE
+unsigned long long* timeline_slot(int kind);  // api.cu: next entry {start, ~end}, both initialised to all-ones
+__device__ __forceinline__ void tl_start(unsigned long long* tl) {
+  if (tl && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); atomicMin(tl, t); }
+}
+__device__ __forceinline__ void tl_end(unsigned long long* tl) {
+  if (tl && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); atomicMin(tl + 1, ~t); }
+}
+#define KVC_TL_SLOT(kind) timeline_slot(kind)
+#else
+__device__ __forceinline__ void tl_start(unsigned long long*) {}
+__device__ __forceinline__ void tl_end(unsigned long long*) {}
+#define KVC_TL_SLOT(kind) nullptr
+#endif
+
 }  // namespace kvc

@@ -20,7 +20,8 @@ __global__ void __launch_bounds__(kGatherThreads)
 gather_rows_kernel(RowSrc ksrc, RowSrc vsrc, const int32_t* __restrict__ idx, int64_t idx_stride,
                    const int32_t* __restrict__ cap, const int32_t* __restrict__ cu_klen,
                    int Hq, int groups, int L, int w, int n_sel, int chunks_per_row,
-                   char* __restrict__ out_k, char* __restrict__ out_v) {
+                   char* __restrict__ out_k, char* __restrict__ out_v, unsigned long long* tl) {
+  tl_start(tl);
   const int unit = blockIdx.y;
   const int b = unit / Hq, h = unit % Hq;
   const int nsel = kVarlen ? cap[h] : n_sel;
@@ -31,38 +32,43 @@ gather_rows_kernel(RowSrc ksrc, RowSrc vsrc, const int32_t* __restrict__ idx, in
   const int rg = threadIdx.x / chunks_per_row;
   if (rg >= rows_per_pass) return;
   const int block_rows = rows_per_pass * kGatherUnroll;
-  const int r0 = blockIdx.x * block_rows + rg;
-  if (blockIdx.x * block_rows >= rows) return;
 
   const int64_t rowbytes = (int64_t)chunks_per_row * 16;
   const char* kbase = ksrc.base + b * ksrc.sb + (h / groups) * ksrc.sh + c * 16;
   const char* vbase = vsrc.base + b * vsrc.sb + (h / groups) * vsrc.sh + c * 16;
   const int32_t* my_idx = idx ? idx + (int64_t)unit * idx_stride : nullptr;
 
-  int srow[kGatherUnroll];
+  // (grid-stride so that a caller may launch fewer CTAs than row blocks; the shipped launches cover them all.
+  // A one-CTA-per-SM "background" grid next to the next layer's select was measured: both kernels slow down
+  // by more than the overlap gains -- they share the LSU/MIO path -- 540 vs 513 us for 8 cfg-2 layers.)
+  for (int blk = blockIdx.x; blk * block_rows < rows; blk += gridDim.x) {
+    const int r0 = blk * block_rows + rg;
+    int srow[kGatherUnroll];
 #pragma unroll
-  for (int u = 0; u < kGatherUnroll; ++u) {
-    const int r = r0 + u * rows_per_pass;
-    int s = -1;
-    if (r < rows) s = (r < nsel) ? (my_idx ? my_idx[r] : r) : (L - w + (r - nsel));
-    srow[u] = s;
-  }
-  int4 kv[kGatherUnroll], vv[kGatherUnroll];
+    for (int u = 0; u < kGatherUnroll; ++u) {
+      const int r = r0 + u * rows_per_pass;
+      int s = -1;
+      if (r < rows) s = (r < nsel) ? (my_idx ? my_idx[r] : r) : (L - w + (r - nsel));
+      srow[u] = s;
+    }
+    int4 kv[kGatherUnroll], vv[kGatherUnroll];
 #pragma unroll
-  for (int u = 0; u < kGatherUnroll; ++u) {
-    if (srow[u] >= 0) {
-      kv[u] = ld_stream16(kbase + (int64_t)srow[u] * ksrc.sl);
-      vv[u] = ld_stream16(vbase + (int64_t)srow[u] * vsrc.sl);
+    for (int u = 0; u < kGatherUnroll; ++u) {
+      if (srow[u] >= 0) {
+        kv[u] = ld_stream16(kbase + (int64_t)srow[u] * ksrc.sl);
+        vv[u] = ld_stream16(vbase + (int64_t)srow[u] * vsrc.sl);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kGatherUnroll; ++u) {
+      if (srow[u] >= 0) {
+        const int64_t off = (out_row0 + r0 + u * rows_per_pass) * rowbytes + c * 16;
+        st_stream16(out_k + off, kv[u]);
+        st_stream16(out_v + off, vv[u]);
+      }
     }
   }
-#pragma unroll
-  for (int u = 0; u < kGatherUnroll; ++u) {
-    if (srow[u] >= 0) {
-      const int64_t off = (out_row0 + r0 + u * rows_per_pass) * rowbytes + c * 16;
-      st_stream16(out_k + off, kv[u]);
-      st_stream16(out_v + off, vv[u]);
-    }
-  }
+  tl_end(tl);
 }
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -90,7 +96,7 @@ int gather_dense(const void* k, int64_t k_sb, int64_t k_sh, int64_t k_sl, const 
   dim3 grid((rows + block_rows - 1) / block_rows, B * Hq);
   RowSrc ks{(const char*)k, k_sb * e, k_sh * e, k_sl * e}, vs{(const char*)v, v_sb * e, v_sh * e, v_sl * e};
   gather_rows_kernel<false><<<grid, kGatherThreads, 0, stream>>>(ks, vs, idx, n_sel, nullptr, nullptr, Hq, Hq / Hkv,
-                                                                  L, w, n_sel, cpr, (char*)out_k, (char*)out_v);
+                                                                  L, w, n_sel, cpr, (char*)out_k, (char*)out_v, KVC_TL_SLOT(2));
   return launch_status("gather_rows_kernel<dense>");
 }
 
@@ -106,7 +112,7 @@ int gather_varlen(const void* k, int64_t k_sh, int64_t k_sl, const void* v, int6
   dim3 grid((rows + block_rows - 1) / block_rows, Hq);
   RowSrc ks{(const char*)k, 0, k_sh * e, k_sl * e}, vs{(const char*)v, 0, v_sh * e, v_sl * e};
   gather_rows_kernel<true><<<grid, kGatherThreads, 0, stream>>>(ks, vs, idx, idx_stride, cap, cu_klen, Hq, Hq / Hkv,
-                                                                 L, w, 0, cpr, (char*)out_k, (char*)out_v);
+                                                                 L, w, 0, cpr, (char*)out_k, (char*)out_v, KVC_TL_SLOT(2));
   return launch_status("gather_rows_kernel<varlen>");
 }
 

@@ -45,6 +45,7 @@ struct Params {
   int reduce_mean;
   float2* stats;        // [units][nchunks][RB*128]
   uint16_t* out;        // [B,Hq,L-w]
+  unsigned long long* tl;  // developer timeline entry (TRACE builds), else nullptr
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -253,6 +254,7 @@ window_score_fused_kernel(const __grid_constant__ CUtensorMap tmap_k, const Para
   float2* xstat = reinterpret_cast<float2*>(smem + SM::kXstatOff);
 
   KVC_STAMP(tid == 0, 0);
+  tl_start(p.tl);
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(kfull(s), 1); mbar_init(kempty(s), 1); }
     for (int i = 0; i < kNumBuf; ++i) { mbar_init(tfull(i), 1); mbar_init(tempty(i), kEpiWarps); }
@@ -519,6 +521,7 @@ window_score_fused_kernel(const __grid_constant__ CUtensorMap tmap_k, const Para
     if (c >= 0) for (int i = tid; i < 64 * 8; i += kThreads) g_tile_trace[c][i / 8][i % 8] = s_tile_trace[i / 8][i % 8];
   }
 #endif
+  tl_end(p.tl);
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -659,6 +662,7 @@ int window_scores_fused(const void* q, int64_t q_sb, int64_t q_sh, int64_t q_sl,
   sp.reduce_mean = reduce == KVC_REDUCE_MEAN;
   sp.stats = (float2*)workspace;
   sp.out = (uint16_t*)out_scores;
+  sp.tl = KVC_TL_SLOT(0);
   const int units = B * Hkv;
   if (dtype == KVC_BF16)
     return pl.rb == 1 ? dispatch_w<Bf16, 1>(tmap, sp, units, stream) : dispatch_w<Bf16, 2>(tmap, sp, units, stream);

@@ -147,7 +147,8 @@ template <typename T, int E, int POOL>
 __global__ void __launch_bounds__(kThreads)
 topk_cluster_kernel(const uint16_t* __restrict__ scores, int n, int kernel_size, int k_fixed,
                     const int32_t* __restrict__ k_per_row, int32_t* __restrict__ out_idx, int64_t idx_stride,
-                    uint16_t* __restrict__ out_pooled, float* __restrict__ out_sums) {
+                    uint16_t* __restrict__ out_pooled, float* __restrict__ out_sums, unsigned long long* tl) {
+  tl_start(tl);
   constexpr int SL = kThreads * E;          // slice length
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Shared& sh = *reinterpret_cast<Shared*>(smem_raw);
@@ -332,6 +333,7 @@ topk_cluster_kernel(const uint16_t* __restrict__ scores, int n, int kernel_size,
       out_sums[2 * row + 1] = bsum;
     }
     cluster_sync();
+    tl_end(tl);
     return;
   }
 
@@ -436,6 +438,7 @@ topk_cluster_kernel(const uint16_t* __restrict__ scores, int n, int kernel_size,
   }
   SEL_STAMP(8);
   cluster_sync();  // keep every CTA's shared memory alive until CTA 0 has read the partial sums
+  tl_end(tl);
 }
 
 template <typename T, int E, int POOL>
@@ -461,7 +464,8 @@ static int launch(const void* scores, int rows, int n, int C, int kernel_size, i
   cfg.numAttrs = 1;
   const uint16_t* sc = (const uint16_t*)scores;
   uint16_t* op = (uint16_t*)out_pooled;
-  KVC_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, sc, n, kernel_size, k, k_per_row, out_idx, idx_stride, op, out_sums));
+  unsigned long long* tl = KVC_TL_SLOT(1);
+  KVC_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, sc, n, kernel_size, k, k_per_row, out_idx, idx_stride, op, out_sums, tl));
   return launch_status("topk_cluster_kernel");
 }
 

@@ -14,7 +14,7 @@ idx = [_native.pool_topk(sc[i], 7, "avgpool", 2016)[0] for i in range(N)]
 torch.cuda.synchronize()
 hi, lo = torch.cuda.Stream(priority=-1), torch.cuda.Stream(priority=0)
 
-def build(do_s, do_g, do_sel):
+def build(do_s, do_g, do_sel, sel_on_hi=False):
     gr = torch.cuda.CUDAGraph()
     cap = torch.cuda.Stream()
     cap.wait_stream(torch.cuda.current_stream())
@@ -25,9 +25,13 @@ def build(do_s, do_g, do_sel):
             if do_s:
                 with torch.cuda.stream(hi):
                     keep += [_native.window_scores(Q, Ks[i], 32, "sum", 0) for i in range(N)]
+            if sel_on_hi and do_sel:
+                with torch.cuda.stream(hi):
+                    for i in range(N):
+                        keep.append(_native.pool_topk(sc[i], 7, "avgpool", 2016)[0])
             with torch.cuda.stream(lo):
                 for i in range(N):
-                    if do_sel: keep.append(_native.pool_topk(sc[i], 7, "avgpool", 2016)[0])
+                    if do_sel and not sel_on_hi: keep.append(_native.pool_topk(sc[i], 7, "avgpool", 2016)[0])
                     if do_g: keep.append(_native.gather_dense(Ks[i], Vs[i], idx[i], 32, 2016, 32))
             cap.wait_stream(hi); cap.wait_stream(lo)
     torch.cuda.current_stream().wait_stream(cap)
@@ -42,6 +46,7 @@ def t(gr):
     return a.elapsed_time(b) * 1e3 / 5 / N
 
 for name, cfg in (("scores alone", (1, 0, 0)), ("gather alone", (0, 1, 0)), ("select alone", (0, 0, 1)),
-                  ("scores || gather", (1, 1, 0)), ("scores || select", (1, 0, 1)), ("scores || select+gather", (1, 1, 1))):
+                  ("scores || gather", (1, 1, 0)), ("scores || select", (1, 0, 1)), ("scores || select+gather", (1, 1, 1)),
+                  ("select || gather", (0, 1, 1, True))):
     gr, keep = build(*cfg)
     print(f"{name:26s} {t(gr):7.1f} us per layer")
