@@ -6,6 +6,7 @@ AdaKV cache append).  The Python classes keep the reference's names and signatur
 done by hand-written CUDA kernels in ``libkvc_b200.so`` behind a C ABI (``include/kvc_b200.h``).
 Importing the package does not need a GPU; calling any ``update_kv`` does.
 """
+from .monkeypatch import replace_llama, replace_mistral  # noqa: F401
 from .pyramidkv_utils import (  # noqa: F401
     AdaKVCluster,
     DynamicCacheSplitHeadFlatten,
@@ -28,5 +29,5 @@ from .pyramidkv_utils import (  # noqa: F401
 __all__ = [
     "AdaKVCluster", "DynamicCacheSplitHeadFlatten", "H2OKVCluster", "HeadKVCluster", "init_headkv", "PyramidKVCluster", "SnapKVCluster",
     "StreamingLLMKVCluster", "init_adakv", "init_H2O", "init_pyramidkv", "init_snapkv", "init_StreamingLLM",
-    "pyramid_budget", "repeat_kv", "wait_for_compression",
+    "pyramid_budget", "repeat_kv", "wait_for_compression", "replace_llama", "replace_mistral",
 ]

@@ -1,0 +1,224 @@
+"""``replace_llama`` / ``replace_mistral``: the reference's model hooks (``pyramidkv/monkeypatch.py:19-145``)
+for the ``transformers`` release installed today.
+
+The reference patches ``LlamaAttention`` / ``LlamaFlashAttention2`` / ``LlamaSdpaAttention.forward`` with one
+hand-copied forward per (method, attention backend) pair (``pyramidkv/llama_model.py``, ``mistral_model.py``)
+written against transformers 4.44; those classes no longer exist (one ``LlamaAttention`` dispatches through
+``ALL_ATTENTION_FUNCTIONS``), so the reference's layer cannot be imported any more.  This module keeps the
+hook NAMES, SIGNATURES and METHOD STRINGS and installs ONE forward per model family that
+
+* prefill (the layer's cache is empty): attention over the full prompt through HF's own attention
+  interface, then ``self.kv_cluster.update_kv(key_states, query_states, value_states, attention_mask,
+  self.num_key_value_groups)`` -- handed the UN-repeated K/V (the kernels fold the GQA groups, the
+  reference materialises ``repeat_kv`` first, ``llama_model.py:379-380``) -- and stores the compressed
+  ``[B, Hq, cap, d]`` rows in the HF cache (``llama_model.py:399-404``);
+* decode: the new K/V row is expanded to the cache's head count, appended, and the query attends to the
+  compressed cache without a mask, as in the reference (``llama_model.py:405-445``); ``self.kv_seq_len``
+  tracks the true sequence length exactly like the reference does.
+
+Positions: ``generate`` derives ``position_ids`` from the attention mask, so RoPE keeps the true token
+positions even though the cache is shorter than the prompt (the reference overrides
+``prepare_inputs_for_generation`` for the same purpose).  Callers that drive ``model.forward`` by hand must
+pass ``position_ids`` themselves once a cache is compressed.
+
+AdaKV / HeadKV keep per-head lengths in the flattened ``[sum_h len_h, d]`` layout
+(``DynamicCacheSplitHeadFlatten``); their decode step needs ``flash_attn_varlen_func``
+(``llama_model.py:2362-2389``), imported lazily.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, Optional
+
+import torch
+
+from . import pyramidkv_utils as U
+
+DENSE_METHODS = ("pyramidkv", "snapkv", "h2o", "streamingllm")
+FLAT_METHODS = ("adakv", "headkv")
+# methods of the reference that lie outside the hot path rebuilt here ("out of scope")
+UNSUPPORTED = ("cam", "l2norm", "minference", "think")
+
+_ORIGINAL: Dict[type, Callable] = {}
+
+
+def _init_cluster(module, method: str) -> None:
+    """What every reference forward does first (``init_pyramidkv(self, num_hidden_layers=...)`` etc.)."""
+    if method == "pyramidkv":
+        U.init_pyramidkv(module, num_hidden_layers=module.config.num_hidden_layers)
+    elif method == "snapkv":
+        U.init_snapkv(module)
+    elif method == "h2o":
+        U.init_H2O(module)
+    elif method == "streamingllm":
+        U.init_StreamingLLM(module)
+    elif method == "adakv":
+        U.init_adakv(module)
+    elif method == "headkv":
+        U.init_headkv(module)
+
+
+class _GroupsView:
+    """The attention module as seen by HF's attention functions, with a different GQA group count
+    (the compressed cache holds one K/V head per QUERY head)."""
+
+    def __init__(self, module, groups: int):
+        object.__setattr__(self, "_module", module)
+        object.__setattr__(self, "num_key_value_groups", groups)
+
+    def __getattr__(self, name):
+        return getattr(object.__getattribute__(self, "_module"), name)
+
+
+def _layer_keys(past_key_values, layer_idx: int) -> Optional[torch.Tensor]:
+    layers = getattr(past_key_values, "layers", None)
+    if layers is None or layer_idx >= len(layers):
+        return None
+    keys = getattr(layers[layer_idx], "keys", None)
+    if keys is None or not getattr(layers[layer_idx], "is_initialized", True) or keys.numel() == 0:
+        return None
+    return keys
+
+
+def _make_forward(method: str, family):
+    apply_rotary_pos_emb = family.apply_rotary_pos_emb
+    eager_attention_forward = family.eager_attention_forward
+    functions = family.ALL_ATTENTION_FUNCTIONS
+    repeat_kv = family.repeat_kv
+
+    def forward(self, hidden_states, position_embeddings=None, attention_mask=None, past_key_values=None, **kwargs):
+        input_shape = hidden_states.shape[:-1]
+        hidden_shape = (*input_shape, -1, self.head_dim)
+        query_states = self.q_proj(hidden_states).view(hidden_shape).transpose(1, 2)
+        key_states = self.k_proj(hidden_states).view(hidden_shape).transpose(1, 2)
+        value_states = self.v_proj(hidden_states).view(hidden_shape).transpose(1, 2)
+        cos, sin = position_embeddings
+        query_states, key_states = apply_rotary_pos_emb(query_states, key_states, cos, sin)
+        q_len = query_states.shape[-2]
+
+        interface = functions.get_interface(self.config._attn_implementation, eager_attention_forward)
+        extra = dict(kwargs)
+        if hasattr(self.config, "sliding_window") and "sliding_window" not in extra and family.__name__.endswith("mistral"):
+            extra["sliding_window"] = getattr(self.config, "sliding_window", None)
+        common = dict(dropout=0.0 if not self.training else self.attention_dropout, scaling=self.scaling)
+
+        module_for_attention, mask = self, attention_mask
+        if past_key_values is None:                                   # no cache: nothing to compress
+            k_att, v_att = key_states, value_states
+        elif _layer_keys(past_key_values, self.layer_idx) is None:    # ---- prefill ----
+            _init_cluster(self, method)
+            self.kv_seq_len = q_len                                   # llama_model.py:362-376
+            k_att, v_att = key_states, value_states                   # attention sees the whole prompt
+            kc, vc = self.kv_cluster.update_kv(key_states, query_states, value_states, attention_mask,
+                                               self.num_key_value_groups)
+            past_key_values.update(kc, vc, self.layer_idx)
+        else:                                                         # ---- decode ----
+            self.kv_seq_len = getattr(self, "kv_seq_len", 0) + q_len
+            cached = _layer_keys(past_key_values, self.layer_idx)
+            if cached.shape[1] != key_states.shape[1]:                # compressed cache: one K/V head per query head
+                key_states = repeat_kv(key_states, self.num_key_value_groups)
+                value_states = repeat_kv(value_states, self.num_key_value_groups)
+            k_att, v_att = past_key_values.update(key_states, value_states, self.layer_idx)
+            groups = query_states.shape[1] // k_att.shape[1]
+            if groups != self.num_key_value_groups:
+                module_for_attention = _GroupsView(self, groups)
+            if k_att.shape[-2] != self.kv_seq_len:                    # rows were evicted: the prompt-shaped mask no longer applies
+                mask = None
+        attn_output, attn_weights = interface(module_for_attention, query_states, k_att, v_att, mask, **common, **extra)
+        attn_output = attn_output.reshape(*input_shape, -1).contiguous()
+        return self.o_proj(attn_output), attn_weights
+
+    forward.__name__ = f"kvc_{method}_attention_forward"
+    return forward
+
+
+def _make_flat_forward(method: str, family):
+    """AdaKV / HeadKV (``llama_flash_attn2_forward_AdaKV`` / ``_HeadKV``, ``llama_model.py:2229-2393``)."""
+    apply_rotary_pos_emb = family.apply_rotary_pos_emb
+    eager_attention_forward = family.eager_attention_forward
+    functions = family.ALL_ATTENTION_FUNCTIONS
+
+    def forward(self, hidden_states, position_embeddings=None, attention_mask=None, past_key_values=None, **kwargs):
+        input_shape = hidden_states.shape[:-1]
+        bsz, q_len = input_shape
+        hidden_shape = (*input_shape, -1, self.head_dim)
+        query_states = self.q_proj(hidden_states).view(hidden_shape).transpose(1, 2)
+        key_states = self.k_proj(hidden_states).view(hidden_shape).transpose(1, 2)
+        value_states = self.v_proj(hidden_states).view(hidden_shape).transpose(1, 2)
+        cos, sin = position_embeddings
+        query_states, key_states = apply_rotary_pos_emb(query_states, key_states, cos, sin)
+        num_heads = query_states.shape[1]
+        if past_key_values is None:
+            raise ValueError(f"{method} needs use_cache=True: its decode path reads the flattened per-head cache")
+        # The reference swaps in DynamicCacheSplitHeadFlatten through a patched LlamaModel.forward
+        # (adaptive_LlamaModel_forward, llama_model.py:2420-2430); here the flattened store rides on whatever
+        # cache object HF created for this generate() call.
+        store = past_key_values
+        if not isinstance(store, U.DynamicCacheSplitHeadFlatten):
+            store = past_key_values.__dict__.setdefault("_kvc_flat", U.DynamicCacheSplitHeadFlatten())
+        past_key_values = store
+        if len(past_key_values) <= self.layer_idx:                    # ---- prefill ----
+            _init_cluster(self, method)
+            self.kv_seq_len = q_len
+            interface = functions.get_interface(self.config._attn_implementation, eager_attention_forward)
+            attn_output, attn_weights = interface(self, query_states, key_states, value_states, attention_mask,
+                                                  dropout=0.0, scaling=self.scaling, **kwargs)
+            flat_k, flat_v = self.kv_cluster.update_kv(key_states, query_states, value_states)
+            past_key_values.update(flat_k, flat_v, self.layer_idx)
+            attn_output = attn_output.reshape(*input_shape, -1).contiguous()
+        else:                                                         # ---- decode (llama_model.py:2362-2389) ----
+            from flash_attn import flash_attn_varlen_func
+            assert bsz == 1 and q_len == 1
+            self.kv_seq_len += q_len
+            c = self.kv_cluster
+            groups = num_heads // key_states.shape[1]
+            k_new = U.repeat_kv(key_states, groups)                   # the flattened cache has one segment per query head
+            v_new = U.repeat_kv(value_states, groups)
+            flat_k, flat_v = past_key_values.update(k_new, v_new, self.layer_idx,
+                                                    {"head_lens": c.head_lens, "cu_klen": c.cu_klen})
+            c.klen_sum += num_heads
+            c.max_seqlen_k += 1
+            c.cu_klen += c.cu_offset
+            c.head_lens += 1
+            q = query_states.reshape(-1, 1, self.head_dim)
+            attn_output = flash_attn_varlen_func(q, flat_k.view(-1, 1, self.head_dim), flat_v.view(-1, 1, self.head_dim),
+                                                 c.cu_qlen, c.cu_klen, 1, c.max_seqlen_k, causal=True)
+            attn_output = attn_output.reshape(bsz, num_heads, q_len, self.head_dim).transpose(1, 2)
+            attn_output = attn_output.reshape(bsz, q_len, -1).contiguous()
+            attn_weights = None
+        past_key_values._seen_tokens = self.kv_seq_len
+        return self.o_proj(attn_output), attn_weights
+
+    forward.__name__ = f"kvc_{method}_attention_forward"
+    return forward
+
+
+def _replace(method: str, family, attention_cls) -> None:
+    if method == "fullkv":
+        return
+    if method in UNSUPPORTED:
+        raise NotImplementedError(f"method '{method}' is outside the compression hot path rebuilt here "
+                                  f"(supported: {', '.join(DENSE_METHODS + FLAT_METHODS)}, fullkv)")
+    if method not in DENSE_METHODS + FLAT_METHODS:
+        raise ValueError(f"unknown method '{method}'")
+    _ORIGINAL.setdefault(attention_cls, attention_cls.forward)
+    maker = _make_forward if method in DENSE_METHODS else _make_flat_forward
+    attention_cls.forward = maker(method, family)
+
+
+def replace_llama(method, model_name=None):
+    """Reference ``replace_llama(method, model_name=None)`` (``monkeypatch.py:19-83``)."""
+    import transformers.models.llama.modeling_llama as family
+    _replace(method, family, family.LlamaAttention)
+
+
+def replace_mistral(method):
+    """Reference ``replace_mistral(method)`` (``monkeypatch.py:88-145``)."""
+    import transformers.models.mistral.modeling_mistral as family
+    _replace(method, family, family.MistralAttention)
+
+
+def restore() -> None:
+    """Undo every ``replace_*`` (not in the reference; used by the tests)."""
+    for cls, fwd in _ORIGINAL.items():
+        cls.forward = fwd
+    _ORIGINAL.clear()

@@ -1,0 +1,180 @@
+"""replace_llama / replace_mistral (reference pyramidkv/monkeypatch.py:19-145) under the installed transformers.
+
+CPU tests drive the hook logic with an ORACLE-backed cluster (the product clusters run on CUDA only);
+the GPU test runs the real CUDA path inside a tiny random Llama and checks the cached rows against
+the oracle applied to the tensors the hook handed to ``update_kv``.
+"""
+import pytest
+import torch
+
+transformers = pytest.importorskip("transformers")
+from transformers import LlamaConfig, LlamaForCausalLM, MistralConfig, MistralForCausalLM  # noqa: E402
+
+import kvcache_factory_b200 as kvc  # noqa: E402
+from kvcache_factory_b200 import monkeypatch as MP  # noqa: E402
+from kvcache_factory_b200 import pyramidkv_utils as U  # noqa: E402
+from oracle import kvc_oracle as O  # noqa: E402
+
+
+@pytest.fixture(autouse=True)
+def _restore():
+    yield
+    MP.restore()
+
+
+def tiny(cls=LlamaForCausalLM, cfg_cls=LlamaConfig, dtype=torch.float32, head_dim=16, layers=2, **over):
+    cfg = cfg_cls(vocab_size=97, hidden_size=4 * head_dim, intermediate_size=64, num_hidden_layers=layers,
+                  num_attention_heads=4, num_key_value_heads=2, head_dim=head_dim, max_position_embeddings=4096,
+                  attn_implementation="eager", **over)
+    torch.manual_seed(0)
+    return cls(cfg).to(dtype).eval()
+
+
+class OracleSnap:
+    """SnapKVCluster stand-in on the CPU restatement (test seam: records what the hook passes in)."""
+    calls = []
+
+    def __init__(self, window_size=64, max_capacity_prompt=320, kernel_size=5, pooling="avgpool", merge=None, **_):
+        self.w, self.cap, self.k, self.pool = window_size, max_capacity_prompt, kernel_size, pooling
+
+    def update_kv(self, key_states, query_states, value_states, attention_mask, num_key_value_groups):
+        assert key_states.shape[1] * num_key_value_groups == query_states.shape[1], "hook must pass un-repeated K/V"
+        kc, vc, idx, _ = O.snapkv_update_kv(key_states, query_states, value_states, self.w, self.cap, self.k, self.pool)
+        OracleSnap.calls.append(dict(L=key_states.shape[-2], out=kc.shape))
+        return kc, vc
+
+
+def test_method_strings_and_restore():
+    import transformers.models.llama.modeling_llama as L
+    import transformers.models.mistral.modeling_mistral as M
+    orig_l, orig_m = L.LlamaAttention.forward, M.MistralAttention.forward
+    for m in ("pyramidkv", "snapkv", "h2o", "streamingllm", "adakv", "headkv"):
+        kvc.replace_llama(m)
+        assert L.LlamaAttention.forward is not orig_l and m in L.LlamaAttention.forward.__name__
+        kvc.replace_mistral(m)
+        assert M.MistralAttention.forward is not orig_m
+    kvc.replace_llama("fullkv", model_name="anything")               # reference: no patch for fullkv
+    MP.restore()
+    assert L.LlamaAttention.forward is orig_l and M.MistralAttention.forward is orig_m
+    kvc.replace_llama("fullkv")
+    assert L.LlamaAttention.forward is orig_l
+    for m in ("cam", "l2norm", "think", "minference"):
+        with pytest.raises(NotImplementedError):
+            kvc.replace_llama(m)
+    with pytest.raises(ValueError):
+        kvc.replace_mistral("nope")
+
+
+@pytest.mark.parametrize("family", ["llama", "mistral"])
+def test_passthrough_equals_plain_transformers(family):
+    """Prompt shorter than max_capacity_prompt: update_kv returns its inputs, generation is unchanged."""
+    model = tiny() if family == "llama" else tiny(MistralForCausalLM, MistralConfig)
+    ids = torch.randint(0, 97, (1, 40), generator=torch.Generator().manual_seed(1))
+    ref = model.generate(ids, max_new_tokens=6, do_sample=False, use_cache=True)
+    (kvc.replace_llama if family == "llama" else kvc.replace_mistral)("snapkv")
+    model.config.max_capacity_prompt, model.config.window_size = 64, 8
+    out = model.generate(ids, max_new_tokens=6, do_sample=False, use_cache=True)
+    assert torch.equal(out, ref)
+
+
+def test_compressed_cache_flow_on_cpu(monkeypatch):
+    """Prefill stores [B,Hq,cap,d]; every decode step appends one row per query head; RoPE positions are the
+    true token positions (generate == a hand-driven loop with explicit position_ids)."""
+    monkeypatch.setattr(U, "SnapKVCluster", OracleSnap)
+    OracleSnap.calls.clear()
+    model = tiny()
+    kvc.replace_llama("snapkv")
+    model.config.max_capacity_prompt, model.config.window_size, model.config.kernel_size = 24, 8, 5
+    L, new = 50, 5
+    ids = torch.randint(0, 97, (1, L), generator=torch.Generator().manual_seed(2))
+    out = model.generate(ids, max_new_tokens=new, do_sample=False, use_cache=True, return_dict_in_generate=True,
+                         output_logits=True)
+    assert [c["L"] for c in OracleSnap.calls] == [L, L] and all(c["out"] == (1, 4, 24, 16) for c in OracleSnap.calls)
+    cache = out.past_key_values
+    # prefill kept 24 rows; the last generated token is never fed back, so new-1 rows were appended
+    assert cache.layers[0].keys.shape == (1, 4, 24 + new - 1, 16)
+    assert model.model.layers[0].self_attn.kv_seq_len == L + new - 1
+    # hand-driven reference: same patched model, explicit positions
+    OracleSnap.calls.clear()
+    from transformers import DynamicCache
+    pkv = DynamicCache(config=model.config)
+    with torch.no_grad():
+        o = model(input_ids=ids, past_key_values=pkv, use_cache=True)
+        logits = [o.logits[:, -1]]
+        tok = logits[-1].argmax(-1, keepdim=True)
+        for t in range(new - 1):
+            o = model(input_ids=tok, position_ids=torch.tensor([[L + t]]), past_key_values=pkv, use_cache=True)
+            logits.append(o.logits[:, -1])
+            tok = logits[-1].argmax(-1, keepdim=True)
+    for a, b in zip(out.logits, logits):
+        assert torch.allclose(a, b, atol=1e-5)
+
+
+@pytest.mark.gpu
+def test_snapkv_hook_runs_cuda_path_in_a_tiny_llama():
+    dev = torch.device("cuda:0")
+    model = tiny(dtype=torch.bfloat16, head_dim=128).to(dev)
+    kvc.replace_llama("snapkv")
+    w, cap, ks = 32, 128, 7
+    model.config.max_capacity_prompt, model.config.window_size, model.config.kernel_size = cap, w, ks
+    model.config.pooling = "avgpool"
+    captured = []
+    orig = U.SnapKVCluster.update_kv
+
+    def spy(self, key_states, query_states, value_states, attention_mask, groups):
+        self.keep_debug = True
+        out = orig(self, key_states, query_states, value_states, attention_mask, groups)
+        captured.append((key_states.detach().cpu(), query_states.detach().cpu(), value_states.detach().cpu(),
+                         self.debug["indices"].cpu().long(), out[0].detach().cpu()))
+        return out
+
+    U.SnapKVCluster.update_kv = spy
+    try:
+        L, new = 700, 4
+        ids = torch.randint(0, 97, (1, L), generator=torch.Generator().manual_seed(3)).to(dev)
+        out = model.generate(ids, max_new_tokens=new, do_sample=False, use_cache=True, return_dict_in_generate=True)
+    finally:
+        U.SnapKVCluster.update_kv = orig
+    torch.cuda.synchronize()
+    assert len(captured) == 2
+    for K, Q, V, idx, Kc in captured:
+        assert K.shape == (1, 2, L, 128) and Q.shape == (1, 4, L, 128)      # un-repeated K/V reach the kernels
+        _, _, idx_ref, pooled_ref = O.snapkv_update_kv(K, Q, V, w, cap, ks, "avgpool")
+        ok, msg = O.check_index_sets(pooled_ref, idx, idx_ref.shape[-1], rtol=2.0 ** -6)
+        assert ok, msg
+        Kr = O.repeat_kv(K, 2)
+        want = torch.cat([Kr[:, :, :-w].gather(2, idx.unsqueeze(-1).expand(-1, -1, -1, 128)), Kr[:, :, -w:]], 2)
+        assert torch.equal(Kc, want)
+    cache = out.past_key_values
+    assert cache.layers[0].keys.shape == (1, 4, cap + new - 1, 128)
+    assert out.sequences.shape == (1, L + new)
+
+
+@pytest.mark.gpu
+def test_adakv_hook_flattened_cache_and_varlen_decode():
+    pytest.importorskip("flash_attn")
+    dev = torch.device("cuda:0")
+    model = tiny(dtype=torch.bfloat16, head_dim=128).to(dev)
+    kvc.replace_llama("adakv")
+    w, cap = 32, 128
+    c = model.config
+    c.max_capacity_prompt, c.window_size, c.kernel_size, c.pooling, c.floor, c.normalize = cap, w, 7, "maxpool", 0.2, True
+    L, new = 700, 4
+    ids = torch.randint(0, 97, (1, L), generator=torch.Generator().manual_seed(4)).to(dev)
+    out = model.generate(ids, max_new_tokens=new, do_sample=False, use_cache=True, return_dict_in_generate=True,
+                         output_logits=True)
+    torch.cuda.synchronize()
+    assert out.sequences.shape == (1, L + new) and all(torch.isfinite(l.float()).all() for l in out.logits)
+    flat = out.past_key_values._kvc_flat
+    for layer in model.model.layers:
+        a = layer.self_attn
+        cl = a.kv_cluster
+        assert a.kv_seq_len == L + new - 1
+        # per-head lengths: budget + window at prefill, +1 per decode step; the flattened tensors hold exactly that
+        lens = cl.head_lens.cpu()
+        assert int(lens.sum()) == cl.klen_sum == flat.key_cache[a.layer_idx].shape[0]
+        # AdaKV reallocates the H*base budget across heads; round() per head may move the total by < 1 row per head
+        assert abs(int(lens.sum()) - (4 * (cap - w) + 4 * w + 4 * (new - 1))) <= 4
+        assert int(lens.min()) >= int((cap - w) * 0.2) + w + new - 1
+        assert torch.equal(cl.cu_klen.cpu()[1:] - cl.cu_klen.cpu()[:-1], lens)
+        assert cl.max_seqlen_k >= int(lens.max())
