@@ -101,8 +101,11 @@ int kvc_h2o_scores(const void* q, int64_t q_sb, int64_t q_sh, int64_t q_sl,
  *   k_per_row == NULL : every row selects `k` entries, out_idx row stride = idx_stride (>= k)
  *   k_per_row != NULL : device int32[rows]; row r selects k_per_row[r] <= k_max = k entries
  * out_pooled (optional, may be NULL): [rows, n] dtype, the pooled scores the selection was made on.
- * out_sums (optional, may be NULL): float[rows,2] = {fp32 sum of the selected values in output
- * order, fp32 sum of all pooled values} (AdaKV ratio normalisation, pyramidkv_utils.py:709-711).
+ * out_sums (optional, may be NULL): float[rows,2] = {fp32 sum of the selected values, fp32 sum of
+ * all pooled values} (AdaKV ratio normalisation, pyramidkv_utils.py:709-711).
+ *   out_idx == NULL with k > 0 and out_sums != NULL: "sums only" -- the kernel stops after the
+ *   threshold search (no compaction, no sort, no indices); KVC_ERR_UNSUPPORTED for shapes outside the
+ *   cluster kernel (k > 8192, n > 131072, kernel_size > 7), where the caller passes an index buffer.
  * ---------------------------------------------------------------------------------------------- */
 size_t kvc_pool_topk_workspace_bytes(int rows, int n, int k);
 int kvc_pool_topk(const void* scores, int rows, int n, int dtype, int kernel_size, int pool,
@@ -118,6 +121,8 @@ int kvc_pool_topk(const void* scores, int rows, int n, int dtype, int kernel_siz
  * out_k/out_v: contiguous [B,Hq,n_sel+w,d].  Row r < n_sel of head h copies K[b, h/(Hq/Hkv),
  * idx[b,h,r], :]; rows n_sel.. copy the last w rows.  idx: int32 [B,Hq,n_sel], values in [0,L-w).
  * Bytes move untouched (bit-exact); elem_bytes in {2,4}.
+ * v (and only v) may point into PINNED host memory: V is read at the selected rows only, so a caller
+ * whose KV lives in host memory need not move the rest of V to the device (unified addressing).
  * ---------------------------------------------------------------------------------------------- */
 int kvc_gather_dense(const void* k, int64_t k_sb, int64_t k_sh, int64_t k_sl,
                      const void* v, int64_t v_sb, int64_t v_sh, int64_t v_sl,
