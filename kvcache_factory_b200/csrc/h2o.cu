@@ -25,7 +25,8 @@ constexpr int kHalfBytes = kTile * 64 * 2;
 constexpr int kTileBytes = 2 * kHalfBytes;
 constexpr int kNumBuf = 4;
 constexpr int kStages = 5;
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = 16;  // 4 warpgroups; warpgroup g owns columns [32g, 32g+32) of every accumulator tile (as scores_fused.cu)
+constexpr int kNumWG = kEpiWarps / 4;
 constexpr int kThreads = 32 * (2 + kEpiWarps);
 constexpr int kMaxGroups = 8;
 
@@ -105,33 +106,78 @@ struct Smem {
   static constexpr int kBarOff = kStatBytes + kRingBytes;
   static constexpr int kNumBars = 2 * kStages + 2 * kNumBuf + 1;
   static constexpr int kTmemPtrOff = kBarOff + kNumBars * 8;
-  static constexpr int kAuxOff = (kTmemPtrOff + 4 + 15) & ~15;  // pass 1: float2[2][128]; pass 2: float[2][8][128]
-  static constexpr int kTotal = kAuxOff + 2 * kMaxGroups * 128 * 4;
+  static constexpr int kAuxOff = (kTmemPtrOff + 4 + 15) & ~15;  // pass 1: float2[kNumWG][128]; pass 2: float[kNumWG][8][128]
+  static constexpr int kTotal = kAuxOff + kNumWG * kMaxGroups * 128 * 4;
   static constexpr int kAlloc = kTotal + 1024;
 };
 
-// Load TMEM accumulator (4 x 32 columns) and apply the reference's two roundings -> 64 packed pairs.
-template <typename T>
-__device__ __forceinline__ void load_round(uint32_t taddr, float scale, uint32_t (&r2)[64], uint32_t tempty_bar, int lane) {
-  uint32_t v[4][32];
-#pragma unroll
-  for (int cc = 0; cc < 4; ++cc) tmem_ld32(taddr + cc * 32, v[cc]);
-  tmem_ld_wait();
-  tc_fence_before();
-  __syncwarp();
-  if (lane == 0) mbar_arrive(tempty_bar);
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
+constexpr float kTau = 6.0f;  // lazy running maximum, see scores_fused.cu
+
+// Pass 1, one chunk of 32 keys of this thread's query row: the reference's two roundings (GEMM result
+// -> dtype, * 1/sqrt(d) in fp32 -> dtype), lazy max, Z += sum exp(x - m_ref).
+template <typename T, bool MASK>
+__device__ __forceinline__ void p1_chunk(const uint32_t (&v)[32], float scale, float& m_ref, float2 (&zacc)[4], int key0,
+                                         int last_key) {
   const float2 scale2 = make_float2(scale, scale);
+  const float2 l2e2 = make_float2(kLog2e, kLog2e);
+  uint32_t r2[16];
 #pragma unroll
-  for (int cc = 0; cc < 4; ++cc) {
-    uint32_t p1[16];
-    float2 f[16];
-#pragma unroll
-    for (int pi = 0; pi < 16; ++pi) p1[pi] = T::pack(__uint_as_float(v[cc][2 * pi]), __uint_as_float(v[cc][2 * pi + 1]));
-#pragma unroll
-    for (int pi = 0; pi < 16; ++pi) f[pi] = __fmul2_rn(make_float2(T::lo(p1[pi]), T::hi(p1[pi])), scale2);
-#pragma unroll
-    for (int pi = 0; pi < 16; ++pi) r2[cc * 16 + pi] = T::pack(f[pi].x, f[pi].y);
+  for (int i = 0; i < 16; ++i) {
+    const float2 f = __fmul2_rn(make_float2(T::rnd(__uint_as_float(v[2 * i])), T::rnd(__uint_as_float(v[2 * i + 1]))), scale2);
+    r2[i] = T::pack(f.x, f.y);
   }
+  if (MASK) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int key = key0 + 2 * i;
+      if (key > last_key) r2[i] = (r2[i] & 0xffff0000u) | (T::kNegInfPair & 0xffffu);
+      if (key + 1 > last_key) r2[i] = (r2[i] & 0x0000ffffu) | (T::kNegInfPair & 0xffff0000u);
+    }
+  }
+  uint32_t pm = r2[0];
+#pragma unroll
+  for (int i = 1; i < 16; ++i) pm = T::max2(pm, r2[i]);
+  const float cm = fmaxf(T::lo(pm), T::hi(pm));
+  if (__any_sync(0xffffffffu, cm > m_ref + kTau)) {
+    const float m_new = cm > m_ref + kTau ? cm : m_ref;
+    const float sc = fast_exp2((m_ref - m_new) * kLog2e);
+    const float2 sc2 = make_float2(sc, sc);
+#pragma unroll
+    for (int a = 0; a < 4; ++a) zacc[a] = __fmul2_rn(zacc[a], sc2);
+    m_ref = m_new;
+  }
+  const float2 ml2 = make_float2(-m_ref * kLog2e, -m_ref * kLog2e);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float2 a = __ffma2_rn(make_float2(T::lo(r2[i]), T::hi(r2[i])), l2e2, ml2);
+    zacc[i & 3] = __fadd2_rn(zacc[i & 3], make_float2(fast_exp2(a.x), fast_exp2(a.y)));
+  }
+}
+
+// Pass 2, one chunk of 32 query rows of this thread's key: p = exp2(x*log2e + c_row) rounded to dtype, summed in fp32.
+template <typename T>
+__device__ __forceinline__ float p2_chunk(const uint32_t (&v)[32], float scale, const float4* __restrict__ cg) {
+  const float2 scale2 = make_float2(scale, scale);
+  const float2 l2e2 = make_float2(kLog2e, kLog2e);
+  float2 acc[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+#pragma unroll
+  for (int q4 = 0; q4 < 8; ++q4) {
+    const float4 c4 = __ldg(cg + q4);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int i = 2 * q4 + h;
+      float2 f = __fmul2_rn(make_float2(T::rnd(__uint_as_float(v[2 * i])), T::rnd(__uint_as_float(v[2 * i + 1]))), scale2);
+      f = __ffma2_rn(make_float2(T::rnd(f.x), T::rnd(f.y)), l2e2, h == 0 ? make_float2(c4.x, c4.y) : make_float2(c4.z, c4.w));
+      acc[h] = __fadd2_rn(acc[h], make_float2(T::rnd(fast_exp2(f.x)), T::rnd(fast_exp2(f.y))));
+    }
+  }
+  return (acc[0].x + acc[0].y) + (acc[1].x + acc[1].y);
 }
 
 template <typename T, bool kPass2>
@@ -162,7 +208,7 @@ h2o_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ C
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(kfull(s), 1); mbar_init(kempty(s), 1); }
-    for (int i = 0; i < kNumBuf; ++i) { mbar_init(tfull(i), 1); mbar_init(tempty(i), 4); }
+    for (int i = 0; i < kNumBuf; ++i) { mbar_init(tfull(i), 1); mbar_init(tempty(i), kEpiWarps); }
     mbar_init(sbar, kPass2 ? 1 : kEpiWarps * 32);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -173,7 +219,7 @@ h2o_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ C
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if constexpr (kPass2) {
-    for (int i = tid; i < 2 * kMaxGroups * 128; i += kThreads) aux[i] = 0.f;
+    for (int i = tid; i < kNumWG * kMaxGroups * 128; i += kThreads) aux[i] = 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -203,18 +249,21 @@ h2o_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ C
   }
 
   if (warp == 0) {
-    if (lane == 0) {
-      if constexpr (kPass2) {  // stationary K tile
+    // TMA producer: warp-uniform loop, one elected lane issues (see scores_fused.cu)
+    if constexpr (kPass2) {  // stationary K tile
+      if (elect_one()) {
         mbar_expect_tx(sbar, kTileBytes);
         tma_load_4d(stat_s, &tmap_k, sbar, 0, blk * kTile, kvh, b);
         tma_load_4d(stat_s + kHalfBytes, &tmap_k, sbar, 64, blk * kTile, kvh, b);
       }
-      for (int t = 0; t < nitems; ++t) {
-        const int s = t % kStages;
-        mbar_wait(kempty(s), ((t / kStages) & 1) ^ 1);
+      __syncwarp();
+    }
+    int s = 0, ph = 1, hl = 0, rbk = 0;
+    for (int t = 0; t < nitems; ++t) {
+      mbar_wait(kempty(s), ph);
+      if (elect_one()) {
         mbar_expect_tx(kfull(s), kTileBytes);
-        if constexpr (kPass2) {
-          const int hl = t % p.groups, rbk = t / p.groups;  // heads interleaved: both epilogue groups see every head
+        if constexpr (kPass2) {  // heads interleaved: consecutive tiles are the g heads of one query row block
           tma_load_4d(ring_s + s * kTileBytes, &tmap_q, kfull(s), 0, rbk * kTile, kvh * p.groups + hl, b);
           tma_load_4d(ring_s + s * kTileBytes + kHalfBytes, &tmap_q, kfull(s), 64, rbk * kTile, kvh * p.groups + hl, b);
         } else {
@@ -222,112 +271,93 @@ h2o_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ C
           tma_load_4d(ring_s + s * kTileBytes + kHalfBytes, &tmap_k, kfull(s), 64, t * kTile, kvh, b);
         }
       }
+      __syncwarp();
+      if (++s == kStages) { s = 0; ph ^= 1; }
+      if (++hl == p.groups) { hl = 0; ++rbk; }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = instr_desc(T::kDtype == KVC_BF16 ? 1 : 0);
-      mbar_wait(sbar, 0);
+    // MMA issuer: warp-uniform loop, elected lane issues; descriptors stay in uniform registers
+    const uint32_t idesc = instr_desc(T::kDtype == KVC_BF16 ? 1 : 0);
+    mbar_wait(sbar, 0);
+    tc_fence_after();
+    const uint64_t ad0 = smem_desc(stat_s);
+    int s = 0, ph = 0, buf = 0, bph = 1;
+    for (int t = 0; t < nitems; ++t) {
+      mbar_wait(tempty(buf), bph);
+      mbar_wait(kfull(s), ph);
       tc_fence_after();
-      for (int t = 0; t < nitems; ++t) {
-        const int s = t % kStages, buf = t % kNumBuf;
-        mbar_wait(kfull(s), (t / kStages) & 1);
-        mbar_wait(tempty(buf), ((t / kNumBuf) & 1) ^ 1);
-        tc_fence_after();
+      const uint64_t bd0 = smem_desc(ring_s + s * kTileBytes);
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < kD / 16; ++k) {
-          const uint32_t off = (k >> 2) * kHalfBytes + (k & 3) * 32;
+          const uint64_t off = (uint64_t)(((k >> 2) * kHalfBytes + (k & 3) * 32) >> 4);
           // A (M = TMEM lanes) is always the stationary tile: query rows in pass 1, keys in pass 2
-          tc_mma(tmem_base + buf * 128, smem_desc(stat_s + off), smem_desc(ring_s + s * kTileBytes + off), idesc, k > 0);
+          tc_mma(tmem_base + buf * 128, ad0 + off, bd0 + off, idesc, k > 0);
         }
         tc_commit(tfull(buf));
         tc_commit(kempty(s));
       }
+      __syncwarp();
+      if (++s == kStages) { s = 0; ph ^= 1; }
+      if (++buf == kNumBuf) { buf = 0; bph ^= 1; }
     }
   } else {
     const int wg = (warp - 2) >> 2;
     const int quad = warp & 3;
     const int r_loc = quad * 32 + lane;
-    float m_run = -1e30f, z_run = 0.f;
-    const float2 l2e2 = make_float2(kLog2e, kLog2e);
+    const float scale = p.scale;
+    const uint32_t tcol = tmem_base + ((uint32_t)(quad * 32) << 16) + wg * 32;
+    float m_run = -1e30f;
+    float2 zacc[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+    int hl = 0, rbk = 0;
 
-    for (int j = wg; j < nitems; j += 2) {
+    for (int j = 0; j < nitems; ++j) {
       const int buf = j % kNumBuf;
       mbar_wait(tfull(buf), (j / kNumBuf) & 1);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * 128;
-      uint32_t r2[64];
-      load_round<T>(taddr, p.scale, r2, tempty(buf), lane);
+      uint32_t v[32];
+      tmem_ld32(tcol + buf * 128, v);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty(buf));
 
       if constexpr (!kPass2) {
-        // thread <-> query row `row`; columns are keys key0 .. key0+127
-        const int row = blk * kTile + r_loc, key0 = j * kTile;
-        if (key0 + kTile > nscore) {  // tile touches the w x w causal block or runs past L
+        // thread <-> query row `row`; this warpgroup's columns are keys key0 .. key0+31
+        const int row = blk * kTile + r_loc, key0 = j * kTile + wg * 32;
+        if (key0 + 32 > nscore) {  // chunk touches the w x w causal block or runs past L
           const int last_key = min(p.L - 1, row >= nscore ? row : p.L - 1);
-#pragma unroll
-          for (int i = 0; i < 64; ++i) {
-            const int key = key0 + 2 * i;
-            if (key > last_key) r2[i] = (r2[i] & 0xffff0000u) | (T::kNegInfPair & 0xffffu);
-            if (key + 1 > last_key) r2[i] = (r2[i] & 0x0000ffffu) | (T::kNegInfPair & 0xffff0000u);
-          }
+          p1_chunk<T, true>(v, scale, m_run, zacc, key0, last_key);
+        } else {
+          p1_chunk<T, false>(v, scale, m_run, zacc, 0, 0);
         }
-        uint32_t pm = r2[0];
-#pragma unroll
-        for (int i = 1; i < 64; ++i) pm = T::max2(pm, r2[i]);
-        const float m_new = fmaxf(m_run, fmaxf(T::lo(pm), T::hi(pm)));
-        const float2 ml2 = make_float2(-m_new * kLog2e, -m_new * kLog2e);
-        float2 zacc[4];
-        zacc[0] = make_float2(z_run * fast_exp2((m_run - m_new) * kLog2e), 0.f);
-        zacc[1] = zacc[2] = zacc[3] = make_float2(0.f, 0.f);
-#pragma unroll
-        for (int bt = 0; bt < 4; ++bt) {
-          float2 a[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) a[i] = __ffma2_rn(make_float2(T::lo(r2[bt * 16 + i]), T::hi(r2[bt * 16 + i])), l2e2, ml2);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) a[i] = make_float2(fast_exp2(a[i].x), fast_exp2(a[i].y));
-#pragma unroll
-          for (int i = 0; i < 16; ++i) zacc[i & 3] = __fadd2_rn(zacc[i & 3], a[i]);
-        }
-        const float2 z2 = __fadd2_rn(__fadd2_rn(zacc[0], zacc[1]), __fadd2_rn(zacc[2], zacc[3]));
-        m_run = m_new;
-        z_run = z2.x + z2.y;
       } else {
-        // thread <-> key blk*128 + r_loc; columns are the 128 query rows of (head hl, row block rbk)
-        const int hl = j % p.groups, rbk = j / p.groups;
+        // thread <-> key blk*128 + r_loc; this warpgroup's columns are query rows 32*wg.. of (head hl, row block rbk)
         const float4* cg = reinterpret_cast<const float4*>(p.cbuf + ((int64_t)b * p.Hq + kvh * p.groups + hl) * (p.tiles * kTile) +
-                                                            (int64_t)rbk * kTile);
-        float2 acc[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-          float2 a[16];
-#pragma unroll
-          for (int q4 = 0; q4 < 8; ++q4) {
-            const float4 c4 = __ldg(cg + cc * 8 + q4);
-            a[2 * q4] = __ffma2_rn(make_float2(T::lo(r2[cc * 16 + 2 * q4]), T::hi(r2[cc * 16 + 2 * q4])), l2e2,
-                                   make_float2(c4.x, c4.y));
-            a[2 * q4 + 1] = __ffma2_rn(make_float2(T::lo(r2[cc * 16 + 2 * q4 + 1]), T::hi(r2[cc * 16 + 2 * q4 + 1])), l2e2,
-                                       make_float2(c4.z, c4.w));
-          }
-          uint32_t pp[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) pp[i] = T::pack(fast_exp2(a[i].x), fast_exp2(a[i].y));
-#pragma unroll
-          for (int i = 0; i < 16; ++i) acc[i & 1] = __fadd2_rn(acc[i & 1], make_float2(T::lo(pp[i]), T::hi(pp[i])));
-        }
+                                                            (int64_t)rbk * kTile + wg * 32);
         float* slot = aux + (wg * kMaxGroups + hl) * 128 + r_loc;  // only this thread touches this slot
-        *slot += (acc[0].x + acc[0].y) + (acc[1].x + acc[1].y);
+        *slot += p2_chunk<T>(v, scale, cg);
+        if (++hl == p.groups) { hl = 0; ++rbk; }
       }
     }
-    if constexpr (!kPass2) reinterpret_cast<float2*>(aux)[wg * 128 + r_loc] = make_float2(m_run, z_run);
+    if constexpr (!kPass2) {
+      const float2 z2 = __fadd2_rn(__fadd2_rn(zacc[0], zacc[1]), __fadd2_rn(zacc[2], zacc[3]));
+      reinterpret_cast<float2*>(aux)[wg * 128 + r_loc] = make_float2(m_run, z2.x + z2.y);
+    }
   }
 
   tc_fence_before();
   __syncthreads();
   if constexpr (!kPass2) {
     for (int r = tid; r < 128; r += kThreads) {
-      const float2 a = reinterpret_cast<float2*>(aux)[r], c = reinterpret_cast<float2*>(aux)[128 + r];
-      const float mn = fmaxf(a.x, c.x);
-      const float z = a.y * fast_exp2((a.x - mn) * kLog2e) + c.y * fast_exp2((c.x - mn) * kLog2e);
+      float mn = -1e30f, z = 0.f;
+#pragma unroll
+      for (int g = 0; g < kNumWG; ++g) mn = fmaxf(mn, reinterpret_cast<float2*>(aux)[g * 128 + r].x);
+#pragma unroll
+      for (int g = 0; g < kNumWG; ++g) {
+        const float2 a = reinterpret_cast<float2*>(aux)[g * 128 + r];
+        z += a.y * fast_exp2((a.x - mn) * kLog2e);
+      }
       const int row = blk * kTile + r;
       p.cbuf[((int64_t)b * p.Hq + hq) * (p.tiles * kTile) + row] = row < p.L ? (-mn * kLog2e - log2f(z)) : -INFINITY;
     }
@@ -335,7 +365,9 @@ h2o_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ C
     for (int e = tid; e < p.groups * 128; e += kThreads) {
       const int hl = e >> 7, r = e & 127, key = blk * kTile + r;
       if (key < nscore) {
-        const float s = aux[hl * 128 + r] + aux[(kMaxGroups + hl) * 128 + r];
+        float s = 0.f;
+#pragma unroll
+        for (int g = 0; g < kNumWG; ++g) s += aux[(g * kMaxGroups + hl) * 128 + r];  // fixed order: deterministic
         p.out[((int64_t)b * p.Hq + kvh * p.groups + hl) * nscore + key] = T::round1(s);
       }
     }
