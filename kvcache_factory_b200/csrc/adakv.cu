@@ -78,13 +78,25 @@ ada_phase1_kernel(const uint16_t* __restrict__ pooled, const float* __restrict__
 // Sum per-head histograms and find the bin where the descending running count reaches K.
 __global__ void __launch_bounds__(kAdaThreads)
 ada_phase2_kernel(const int* __restrict__ hist1, int H, int K, AdaHeader* hdr) {
-  __shared__ int tot[kAdaBins];
+  __shared__ __align__(16) int tot[kAdaBins];
   __shared__ int warp_sum[32];
   const int tid = threadIdx.x;
-  for (int i = tid; i < kAdaBins; i += kAdaThreads) {
-    int s = 0;
-    for (int h = 0; h < H; ++h) s += hist1[(int64_t)h * kAdaBins + i];
-    tot[i] = s;
+  {  // thread t sums bins [4t, 4t+4) over the heads with 16-byte loads, 8 heads in flight
+    int4 s = make_int4(0, 0, 0, 0);
+    const int4* col = reinterpret_cast<const int4*>(hist1) + tid;
+    int h = 0;
+    for (; h + 8 <= H; h += 8) {
+      int4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldg(col + (int64_t)(h + u) * (kAdaBins / 4));
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w; }
+    }
+    for (; h < H; ++h) {
+      const int4 v = __ldg(col + (int64_t)h * (kAdaBins / 4));
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    *reinterpret_cast<int4*>(&tot[4 * tid]) = s;
   }
   __syncthreads();
   // thread t owns bins [4*(1023-t), +4): an ascending-thread scan walks down from the top bin
@@ -143,44 +155,66 @@ ada_phase3_kernel(const uint16_t* __restrict__ akeys, const int* __restrict__ hi
   if (tid == 0) above[h] = s_above;
 }
 
-__global__ void ada_phase4_kernel(const int* __restrict__ hist2, const int* __restrict__ above, int H, int n, int K,
-                                  float one_minus_floor, int floor_capacity, int w, AdaHeader* hdr,
-                                  int32_t* __restrict__ out_cap, int32_t* __restrict__ out_head_lens,
-                                  int32_t* __restrict__ out_cu_klen) {
-  if (threadIdx.x != 0) return;  // H <= a few hundred heads: a serial pass over tiny tables
-  int tot[16];
-  for (int t = 0; t < 16; ++t) {
-    int s = 0;
-    for (int h = 0; h < H; ++h) s += hist2[h * 16 + t];
-    tot[t] = s;
-  }
+// One warp: lane <-> head (32 heads per round, carried totals across rounds), tiny tables.
+__global__ void __launch_bounds__(32)
+ada_phase4_kernel(const int* __restrict__ hist2, const int* __restrict__ above, int H, int n, int K,
+                  float one_minus_floor, int floor_capacity, int w, AdaHeader* hdr,
+                  int32_t* __restrict__ out_cap, int32_t* __restrict__ out_head_lens,
+                  int32_t* __restrict__ out_cu_klen) {
+  const int lane = threadIdx.x;
+  // exact threshold: totals of the 16 low-bit bins over all heads (lanes 0..15 <-> bins)
+  int tot = 0;
+  if (lane < 16)
+    for (int h = 0; h < H; ++h) tot += hist2[h * 16 + lane];
   int cum = hdr->above_bin, thr_low = 0;
   for (int t = 15; t >= 0; --t) {
-    if (cum + tot[t] >= K) { thr_low = t; break; }
-    cum += tot[t];
+    const int tt = __shfl_sync(0xffffffffu, tot, t);
+    if (cum + tt >= K) { thr_low = t; break; }
+    cum += tt;
   }
-  hdr->thr_key = (hdr->thr_bin << 4) | thr_low;
-  hdr->count_gt = cum;
+  if (lane == 0) { hdr->thr_key = (hdr->thr_bin << 4) | thr_low; hdr->count_gt = cum; }
   int remaining = K - cum;  // ties still to hand out, lowest head index first
   int run = 0;
-  for (int h = 0; h < H; ++h) {
-    int cnt = above[h];
-    for (int t = 15; t > thr_low; --t) cnt += hist2[h * 16 + t];
-    const int eq = hist2[h * 16 + thr_low];
-    const int take = eq < remaining ? eq : remaining;
-    remaining -= take;
+  for (int h0 = 0; h0 < H; h0 += 32) {
+    const int h = h0 + lane;
+    const bool in = h < H;
+    int cnt = 0, eq = 0;
+    if (in) {
+      cnt = above[h];
+      for (int t = 15; t > thr_low; --t) cnt += hist2[h * 16 + t];
+      eq = hist2[h * 16 + thr_low];
+    }
+    int eq_inc = eq;  // inclusive scan of the tie counts over the heads of this round
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, eq_inc, o);
+      if (lane >= o) eq_inc += t;
+    }
+    const int before = eq_inc - eq;
+    const int left = remaining - before;
+    const int take = left <= 0 ? 0 : (eq < left ? eq : left);
+    remaining -= min(remaining, __shfl_sync(0xffffffffu, eq_inc, 31));
     cnt += take;
     // torch.round(count * (1 - floor_ratio) + floor_capacity).int(): two fp32 roundings, half-to-even
     const float v = __fadd_rn(__fmul_rn((float)cnt, one_minus_floor), (float)floor_capacity);
     int cap = (int)rintf(v);
     if (cap > n) cap = n;  // sorted_idx[..., :cap] clamps at the row length
     if (cap < 0) cap = 0;
-    out_cap[h] = cap;
-    out_head_lens[h] = cap + w;
-    out_cu_klen[h] = run;
-    run += cap + w;
+    const int len = in ? cap + w : 0;
+    int len_inc = len;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, len_inc, o);
+      if (lane >= o) len_inc += t;
+    }
+    if (in) {
+      out_cap[h] = cap;
+      out_head_lens[h] = cap + w;
+      out_cu_klen[h] = run + len_inc - len;
+    }
+    run += __shfl_sync(0xffffffffu, len_inc, 31);
   }
-  out_cu_klen[H] = run;
+  if (lane == 0) out_cu_klen[H] = run;
 }
 
 int adakv_allocate(const void* pooled, const float* sums, int H, int n, int dtype, int base_capacity,
