@@ -14,6 +14,8 @@
 //      indices by descending value, ascending position among equal values (torch.topk sorted=True,
 //      deterministic on ties)
 // Rows longer than 16 * 8192 scores or k > 8192 use the one-CTA-per-row kernel in select.cu.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace kvc {
@@ -26,9 +28,7 @@ __device__ long long g_sel_trace[16];
 #define SEL_STAMP(slot) do { } while (0)
 #endif
 
-constexpr int kThreads = 1024;
-constexpr int kWarps = kThreads / 32;
-constexpr int kMaxK = 8192;
+constexpr int kMaxK = 8192;   // 1024-thread variant; the 512-thread variant sorts at most kMaxK / 2 winners
 constexpr int kHalo = 3;  // pooling kernels up to 7 taps
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -47,19 +47,21 @@ __device__ __forceinline__ float ld_cluster_f32(uint32_t a) { float v; asm volat
 __device__ __forceinline__ void st_cluster_u32(uint32_t a, uint32_t v) { asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void st_cluster_u16(uint32_t a, uint16_t v) { asm volatile("st.shared::cluster.u16 [%0], %1;" ::"r"(a), "h"(v) : "memory"); }
 
-struct Shared {
+template <int kWarps>
+struct SharedT {
   int whist[kWarps][256];   // warp-private counters (select rounds: bins; sort: digit offsets)
   int hist[2][256];         // this CTA's per-round histograms, read by the whole cluster
-  int warp_tmp[kWarps];
-  int warp_tmp2[kWarps];
-  float fsum[kWarps];
+  int warp_tmp[32];
+  int warp_tmp2[32];
+  float fsum[32];
   int mm[2];                // min / max key of this CTA's slice
   int totals[2];            // selected-above / equal-to-threshold counts of this CTA
   float psum[2];            // partial sums (selected, all) of this CTA
   int sel_digit, sel_above; // result of the per-round threshold search
 };
 
-// Exclusive block scan of one int per thread (1024 threads).
+// Exclusive block scan of one int per thread (kWarps warps, <= 32).
+template <int kWarps>
 __device__ __forceinline__ int block_scan_excl(int v, int* warp_tmp, int& total) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   int inc = v;
@@ -71,7 +73,7 @@ __device__ __forceinline__ int block_scan_excl(int v, int* warp_tmp, int& total)
   __syncthreads();  // warp_tmp free to overwrite
   if (lane == 31) warp_tmp[wid] = inc;
   __syncthreads();
-  const int mine = warp_tmp[lane];  // kWarps == 32: lane l holds warp l's total
+  const int mine = lane < kWarps ? warp_tmp[lane] : 0;  // lane l holds warp l's total
   int pre = mine;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -83,6 +85,7 @@ __device__ __forceinline__ int block_scan_excl(int v, int* warp_tmp, int& total)
   return base + inc - v;
 }
 
+template <int kWarps>
 __device__ __forceinline__ float block_sum_f(float v, float* tmp) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
@@ -90,7 +93,7 @@ __device__ __forceinline__ float block_sum_f(float v, float* tmp) {
   __syncthreads();
   if (lane == 0) tmp[wid] = v;
   __syncthreads();
-  float r = tmp[lane];
+  float r = lane < kWarps ? tmp[lane] : 0.f;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
   return r;
@@ -110,14 +113,15 @@ __device__ __forceinline__ int warp_rank_digit(int* wh, int digit, int lane) {
 
 // Sum the cluster's per-CTA histograms of `round` and find the bin at which the descending running
 // count reaches krem.  Every CTA computes the same answer.  Threads 0..255 <-> bins 255..0.
-__device__ __forceinline__ void cluster_threshold(Shared& sh, int round, int krem, uint32_t csize, int& digit, int& above) {
+template <int kWarps>
+__device__ __forceinline__ void cluster_threshold(SharedT<kWarps>& sh, int round, int krem, uint32_t csize, int& digit, int& above) {
   const int tid = threadIdx.x;
   const int d = 255 - tid;
   int cnt = 0;
   if (tid < 256)
     for (uint32_t c = 0; c < csize; ++c) cnt += (int)ld_cluster_u32(map_to_rank(&sh.hist[round][d], c));
   int total;
-  const int ex = block_scan_excl(cnt, sh.warp_tmp, total);
+  const int ex = block_scan_excl<kWarps>(cnt, sh.warp_tmp, total);
   if (tid < 256 && ex < krem && ex + cnt >= krem) { sh.sel_digit = d; sh.sel_above = ex; }
   __syncthreads();
   digit = sh.sel_digit;
@@ -125,8 +129,8 @@ __device__ __forceinline__ void cluster_threshold(Shared& sh, int round, int kre
 }
 
 // One counting round: bins of the participating keys -> warp-private atomics -> CTA histogram.
-template <int E>
-__device__ __forceinline__ void count_round(Shared& sh, int round, const int (&bin)[E], int lane, int wid) {
+template <int E, int kWarps>
+__device__ __forceinline__ void count_round(SharedT<kWarps>& sh, int round, const int (&bin)[E], int lane, int wid) {
   int* wh = sh.whist[wid];
 #pragma unroll
   for (int i = lane; i < 256; i += 32) wh[i] = 0;
@@ -143,20 +147,23 @@ __device__ __forceinline__ void count_round(Shared& sh, int round, const int (&b
   }
 }
 
-template <typename T, int E, int POOL>
-__global__ void __launch_bounds__(kThreads)
+template <typename T, int E, int POOL, int kThreads>
+__global__ void __launch_bounds__(kThreads, kThreads == 512 ? 2 : 1)
 topk_cluster_kernel(const uint16_t* __restrict__ scores, int n, int kernel_size, int k_fixed,
                     const int32_t* __restrict__ k_per_row, int32_t* __restrict__ out_idx, int64_t idx_stride,
                     uint16_t* __restrict__ out_pooled, float* __restrict__ out_sums, unsigned long long* tl) {
   tl_start(tl);
   constexpr int SL = kThreads * E;          // slice length
+  constexpr int kWarps = kThreads / 32;
+  constexpr int kMaxKT = kThreads == 1024 ? kMaxK : kMaxK / 2;   // winners the sort buffers of this variant hold
+  using Shared = SharedT<kWarps>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Shared& sh = *reinterpret_cast<Shared*>(smem_raw);
   unsigned char* dyn = smem_raw + ((sizeof(Shared) + 15) & ~15);
   uint16_t* stage = reinterpret_cast<uint16_t*>(dyn);   // phase 1: chunk stride E+2 u16 (odd word stride)
   // phase 3-4 (CTA 0 only, written remotely): keys/indices ping-pong
-  uint16_t* skey[2] = {reinterpret_cast<uint16_t*>(dyn), reinterpret_cast<uint16_t*>(dyn) + kMaxK};
-  uint32_t* sidx[2] = {reinterpret_cast<uint32_t*>(dyn + 4 * kMaxK), reinterpret_cast<uint32_t*>(dyn + 4 * kMaxK) + kMaxK};
+  uint16_t* skey[2] = {reinterpret_cast<uint16_t*>(dyn), reinterpret_cast<uint16_t*>(dyn) + kMaxKT};
+  uint32_t* sidx[2] = {reinterpret_cast<uint32_t*>(dyn + 4 * kMaxKT), reinterpret_cast<uint32_t*>(dyn + 4 * kMaxKT) + kMaxKT};
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const uint32_t crank = cluster_rank(), csize = cluster_size();
@@ -244,7 +251,7 @@ topk_cluster_kernel(const uint16_t* __restrict__ scores, int n, int kernel_size,
   }
   SEL_STAMP(1);
   const int nvalid = max(0, min(E, n - j0));
-  const float sum_all_cta = out_sums ? block_sum_f(part_all, sh.fsum) : 0.f;
+  const float sum_all_cta = out_sums ? block_sum_f<kWarps>(part_all, sh.fsum) : 0.f;
   if (k == 0) {  // uniform over the cluster; nothing to select (AdaKV asks only for pooled scores / sums)
     if (out_sums) {
       if (tid == 0) sh.psum[1] = sum_all_cta;
@@ -271,8 +278,8 @@ topk_cluster_kernel(const uint16_t* __restrict__ scores, int n, int kernel_size,
   if (lane == 0) { sh.warp_tmp[wid] = kmin; sh.warp_tmp2[wid] = kmax; }
   __syncthreads();
   if (wid == 0) {
-    const int a = __reduce_min_sync(0xffffffffu, sh.warp_tmp[lane]);
-    const int b2 = __reduce_max_sync(0xffffffffu, sh.warp_tmp2[lane]);
+    const int a = __reduce_min_sync(0xffffffffu, lane < kWarps ? sh.warp_tmp[lane] : 0xffff);
+    const int b2 = __reduce_max_sync(0xffffffffu, lane < kWarps ? sh.warp_tmp2[lane] : 0);
     if (lane == 0) { sh.mm[0] = a; sh.mm[1] = b2; }
   }
   cluster_sync();
@@ -291,19 +298,19 @@ topk_cluster_kernel(const uint16_t* __restrict__ scores, int n, int kernel_size,
     int bin[E];
 #pragma unroll
     for (int i = 0; i < E; ++i) bin[i] = i < nvalid ? ((int)keys[i] - kmin) >> sh1 : -1;
-    count_round<E>(sh, 0, bin, lane, wid);
+    count_round<E, kWarps>(sh, 0, bin, lane, wid);
     cluster_sync();  // every CTA's hist[0] is complete and visible
     int b1, above;
-    cluster_threshold(sh, 0, krem, csize, b1, above);
+    cluster_threshold<kWarps>(sh, 0, krem, csize, b1, above);
     krem -= above;
     thr_key = kmin + (b1 << sh1);
     if (sh1 > 0) {
 #pragma unroll
       for (int i = 0; i < E; ++i) bin[i] = (bin[i] == b1) ? ((int)keys[i] - thr_key) : -1;
-      count_round<E>(sh, 1, bin, lane, wid);
+      count_round<E, kWarps>(sh, 1, bin, lane, wid);
       cluster_sync();
       int b2v, above2;
-      cluster_threshold(sh, 1, krem, csize, b2v, above2);
+      cluster_threshold<kWarps>(sh, 1, krem, csize, b2v, above2);
       krem -= above2;
       thr_key += b2v;
     }
@@ -318,7 +325,7 @@ topk_cluster_kernel(const uint16_t* __restrict__ scores, int n, int kernel_size,
 #pragma unroll
     for (int i = 0; i < E; ++i)
       if (i < nvalid && (int)keys[i] > thr_key) part_top += T::to_float((uint16_t)key_to_float16_bits(keys[i]));
-    const float st = block_sum_f(part_top, sh.fsum);
+    const float st = block_sum_f<kWarps>(part_top, sh.fsum);
     if (tid == 0) { sh.psum[0] = st; sh.psum[1] = sum_all_cta; }
     cluster_sync();
     if (crank == 0 && tid == 0 && out_sums) {
@@ -345,7 +352,7 @@ topk_cluster_kernel(const uint16_t* __restrict__ scores, int n, int kernel_size,
     eq += (i < nvalid && (int)keys[i] == thr_key);
   }
   int total;
-  const int ex = block_scan_excl(gt | (eq << 16), sh.warp_tmp, total);
+  const int ex = block_scan_excl<kWarps>(gt | (eq << 16), sh.warp_tmp, total);
   if (tid == 0) { sh.totals[0] = total & 0xffff; sh.totals[1] = (int)((uint32_t)total >> 16); }
   SEL_STAMP(5);
   cluster_sync();  // totals visible; also: every CTA is past its last read of `stage`, so CTA 0's buffers are free
@@ -371,7 +378,7 @@ topk_cluster_kernel(const uint16_t* __restrict__ scores, int n, int kernel_size,
     }
   }
   if (out_sums) {
-    const float st = block_sum_f(part_top, sh.fsum);
+    const float st = block_sum_f<kWarps>(part_top, sh.fsum);
     if (tid == 0) { sh.psum[0] = st; sh.psum[1] = sum_all_cta; }
   }
   cluster_sync();  // all winners (and partial sums) have landed in / are readable by CTA 0
@@ -413,7 +420,7 @@ topk_cluster_kernel(const uint16_t* __restrict__ scores, int n, int kernel_size,
         for (int w = 0; w < kWarps; ++w) tot += sh.whist[w][tid];
       }
       int total2;
-      int dbase = block_scan_excl(tot, sh.warp_tmp, total2);
+      int dbase = block_scan_excl<kWarps>(tot, sh.warp_tmp, total2);
       if (tid < 256) {
 #pragma unroll
         for (int w = 0; w < kWarps; ++w) { const int c = sh.whist[w][tid]; sh.whist[w][tid] = dbase; dbase += c; }
@@ -441,12 +448,13 @@ topk_cluster_kernel(const uint16_t* __restrict__ scores, int n, int kernel_size,
   tl_end(tl);
 }
 
-template <typename T, int E, int POOL>
+template <typename T, int E, int POOL, int kThreads = 1024>
 static int launch(const void* scores, int rows, int n, int C, int kernel_size, int k, const int32_t* k_per_row,
                   int32_t* out_idx, int64_t idx_stride, void* out_pooled, float* out_sums, cudaStream_t stream) {
-  auto kern = topk_cluster_kernel<T, E, POOL>;
+  auto kern = topk_cluster_kernel<T, E, POOL, kThreads>;
+  using Shared = SharedT<kThreads / 32>;
   const size_t stage_bytes = (size_t)(kThreads * E + 2 * kHalo + 2 * (kThreads + 2)) * 2;
-  const size_t sort_bytes = (size_t)kMaxK * 12;
+  const size_t sort_bytes = (size_t)(kThreads == 1024 ? kMaxK : kMaxK / 2) * 12;
   const size_t smem = ((sizeof(Shared) + 15) & ~(size_t)15) + (stage_bytes > sort_bytes ? stage_bytes : sort_bytes);
   KVC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (C > 8) KVC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
@@ -475,6 +483,14 @@ static int dispatch_e(const void* scores, int rows, int n, int kernel_size, int 
   // slice = 1024*E scores per CTA
   if (n <= 4096) return launch<T, 4, POOL>(scores, rows, n, 1, kernel_size, k, k_per_row, out_idx, idx_stride, out_pooled, out_sums, stream);
   if (n <= 16384) return launch<T, 4, POOL>(scores, rows, n, (n + 4095) / 4096, kernel_size, k, k_per_row, out_idx, idx_stride, out_pooled, out_sums, stream);
+  // 512-thread variant: 64 registers and ~67 KB of shared memory, so TWO CTAs fit on an SM and the selects of
+  // consecutive layers (issued on rotating side streams by the host mirror) overlap their latency chains:
+  // 10.4 us per layer for two overlapped selects against 15.8 us back to back with the 1024-thread variant,
+  // 16.5 us when alone.  With 3 CTAs per SM (40 registers) the spills cost more than the overlap gains.
+  // KVC_SELECT_THREADS=1024 forces the one-CTA-per-SM variant.
+  static const bool half = [] { const char* e = getenv("KVC_SELECT_THREADS"); return !(e && atoi(e) == 1024); }();
+  if (half && n > 16384 && n <= 32768 && k <= kMaxK / 2)
+    return launch<T, 16, POOL, 512>(scores, rows, n, (n + 8191) / 8192, kernel_size, k, k_per_row, out_idx, idx_stride, out_pooled, out_sums, stream);
   // one CTA occupies a whole SM (1 024 threads): prefer the slice length that keeps rows * C within one wave
   if (n <= 32768 || (n <= 65536 && rows * ((n + 8191) / 8192) <= sm_count()))
     return launch<T, 8, POOL>(scores, rows, n, (n + 8191) / 8192, kernel_size, k, k_per_row, out_idx, idx_stride, out_pooled, out_sums, stream);

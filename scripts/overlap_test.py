@@ -47,6 +47,17 @@ def t(gr):
 
 for name, cfg in (("scores alone", (1, 0, 0)), ("gather alone", (0, 1, 0)), ("select alone", (0, 0, 1)),
                   ("scores || gather", (1, 1, 0)), ("scores || select", (1, 0, 1)), ("scores || select+gather", (1, 1, 1)),
-                  ("select || gather", (0, 1, 1, True))):
-    gr, keep = build(*cfg)
+                  ("select || gather", (0, 1, 1, True)), ("select || select", "selsel")):
+    if cfg == "selsel":
+        gr = torch.cuda.CUDAGraph(); cap = torch.cuda.Stream(); cap.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(cap):
+            with torch.cuda.graph(gr, stream=cap):
+                hi.wait_stream(cap); lo.wait_stream(cap); keep = []
+                for i in range(N):
+                    with torch.cuda.stream(hi if i % 2 == 0 else lo):
+                        keep.append(_native.pool_topk(sc[i], 7, "avgpool", 2016)[0])
+                cap.wait_stream(hi); cap.wait_stream(lo)
+        torch.cuda.current_stream().wait_stream(cap)
+    else:
+        gr, keep = build(*cfg)
     print(f"{name:26s} {t(gr):7.1f} us per layer")
