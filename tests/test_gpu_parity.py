@@ -514,3 +514,32 @@ def test_pyramidkv_full_size_properties(impl):
         assert torch.equal(Vc[:, :, :budget], Vr.gather(2, idx.unsqueeze(-1).expand(-1, -1, -1, 128)))
         # the planted heavy hitters (1 % of positions, +4*qbar) dominate the selection
         del Kr, Vr
+
+
+def test_async_tail_matches_synchronous_path():
+    """async_tail: select and gather of each layer run on rotating side streams (selects of consecutive
+    layers overlap); after wait_for_compression() the results are bit-identical to the synchronous path."""
+    from kvcache_factory_b200 import wait_for_compression
+    shape = Shape(1, 8, 2, 20000, 128)         # n = 19968 scores per row: the 512-thread cluster select
+    w, cap, nl = 32, 2048, 7
+    ins, ref = [], []
+    for l in range(nl):
+        Q, K, V = make_qkv(shape, torch.bfloat16, layer_idx=l, dist="peaked", window=w, q_window_only=True)
+        Qd, Kd, Vd = Q.to(dev()), K.to(dev()), V.to(dev())
+        ins.append((Kd, Qd, Vd))
+        cl = PyramidKVCluster(num_hidden_layers=nl, window_size=w, max_capacity_prompt=cap, kernel_size=7,
+                              pooling="avgpool", layer_idx=l)
+        ref.append(cl.update_kv(Kd, Qd, Vd, None, 4))
+    torch.cuda.synchronize()
+    outs = []
+    for rep in range(2):                          # second round reuses the streams
+        outs = []
+        for l in range(nl):
+            cl = PyramidKVCluster(num_hidden_layers=nl, window_size=w, max_capacity_prompt=cap, kernel_size=7,
+                                  pooling="avgpool", layer_idx=l)
+            cl.async_tail = True
+            outs.append(cl.update_kv(*ins[l], None, 4))
+        wait_for_compression(dev())
+        torch.cuda.current_stream().synchronize()
+        for l in range(nl):
+            assert torch.equal(outs[l][0], ref[l][0]) and torch.equal(outs[l][1], ref[l][1]), f"layer {l} round {rep}"
