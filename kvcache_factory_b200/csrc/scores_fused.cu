@@ -450,16 +450,21 @@ window_score_fused_kernel(const __grid_constant__ CUtensorMap tmap_k, const Para
     }
     epi_sync();
     KVC_STAMP(et == 0, 6);  // grid barrier passed
-    for (int r = et; r < RB * 128; r += kEpiThreads) {
-      const float2* st = p.stats + (int64_t)unit * p.nchunks * (RB * 128) + r;
+    {
+      // fold every chunk's (m, Z): all 512 threads take part -- thread = (row, part), part q folds chunks
+      // q, q+nparts, ... (loads in one or two batches instead of nchunks/8 dependent round trips per row),
+      // the parts meet in shared memory
+      constexpr int kRows = RB * 128, kParts = kEpiThreads / kRows;
+      const int r = et % kRows, q = et / kRows;
+      const float2* st = p.stats + (int64_t)unit * p.nchunks * kRows + r;
       float M = -1e30f, Z = 0.f;
-      for (int c0 = 0; c0 < p.nchunks; c0 += 8) {
+      for (int c0 = q; c0 < p.nchunks; c0 += 8 * kParts) {
         float2 sv[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           sv[u] = make_float2(-1e30f, 0.f);
-          if (c0 + u < p.nchunks) {
-            const float2* a = st + (int64_t)(c0 + u) * (RB * 128);
+          if (c0 + u * kParts < p.nchunks) {
+            const float2* a = st + (int64_t)(c0 + u * kParts) * kRows;
             asm volatile("ld.global.cg.v2.f32 {%0, %1}, [%2];" : "=f"(sv[u].x), "=f"(sv[u].y) : "l"(a) : "memory");  // written by other SMs: bypass L1
           }
         }
@@ -471,7 +476,19 @@ window_score_fused_kernel(const __grid_constant__ CUtensorMap tmap_k, const Para
         for (int u = 0; u < 8; ++u) Z += sv[u].y * fast_exp2((sv[u].x - mx) * kLog2e);
         M = mx;
       }
-      crow[r] = (r / W < p.groups) ? (-M * kLog2e - log2f(Z)) : -INFINITY;
+      xstat[q * kRows + r] = make_float2(M, Z);
+      epi_sync();
+      if (et < kRows) {
+        float mx = -1e30f, z = 0.f;
+#pragma unroll
+        for (int g = 0; g < kParts; ++g) mx = fmaxf(mx, xstat[g * kRows + et].x);
+#pragma unroll
+        for (int g = 0; g < kParts; ++g) {
+          const float2 a = xstat[g * kRows + et];
+          z += a.y * fast_exp2((a.x - mx) * kLog2e);
+        }
+        crow[et] = (et / W < p.groups) ? (-mx * kLog2e - log2f(z)) : -INFINITY;
+      }
     }
     epi_sync();
 
