@@ -31,6 +31,25 @@ def timed(fn, iters=5, warm=2):
     return ts[len(ts) // 2], ts[0]
 
 
+def timed_graph(fn, reps=8, inner=8):
+    """Same call captured `inner` times into one CUDA graph: launch overhead of the Python wrapper excluded."""
+    fn(); torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph(); cap = torch.cuda.Stream(); cap.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(cap):
+        with torch.cuda.graph(g, stream=cap):
+            keep = [fn() for _ in range(inner)]
+    torch.cuda.current_stream().wait_stream(cap)
+    g.replay(); torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); g.replay(); b.record(); torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b) * 1e3 / inner)
+    ts.sort()
+    del keep
+    return ts[len(ts) // 2], ts[0]
+
+
 def emit(name, us_med, us_best, tokens, alg_bytes=None, alg_flops=None, **extra):
     line = {"config": name, "us_per_layer_median": round(us_med, 1), "us_per_layer_best": round(us_best, 1),
             "tokens_per_s_per_layer": round(tokens / (us_med * 1e-6)), **extra}
@@ -49,9 +68,11 @@ def cfg1():
     for dt in (torch.bfloat16, torch.float16):
         cl = SnapKVCluster(w, cap, 7, "avgpool")
         k, v, q = K.to(dt), V.to(dt), Q.to(dt)
-        med, best = timed(lambda: cl.update_kv(k, q, v, None, 4), iters=20)
         alg = B * Hkv * L * d * 2 + B * Hq * w * d * 2 + 4 * B * Hq * cap * d * 2
+        med, best = timed(lambda: cl.update_kv(k, q, v, None, 4), iters=20)
         emit(f"cfg1 SnapKV 8B L=4096 w=32 cap=128 avgpool7 {str(dt)[6:]} (3 launches, eager)", med, best, B * L, alg)
+        med, best = timed_graph(lambda: cl.update_kv(k, q, v, None, 4))
+        emit(f"cfg1 SnapKV 8B L=4096 w=32 cap=128 avgpool7 {str(dt)[6:]} (3 launches, CUDA graph)", med, best, B * L, alg)
 
 
 def cfg3():
@@ -60,7 +81,9 @@ def cfg3():
     Q = rand(B, Hq, L, d, seed=3)
     cl = StreamingLLMKVCluster(w, cap, 7, "avgpool")
     med, best = timed(lambda: cl.update_kv(K, Q, V, None, 4), iters=10)
-    emit("cfg3 StreamingLLM Mistral-7B B=8 L=32768 cap=1024", med, best, B * L, 4 * B * Hq * cap * d * 2)
+    emit("cfg3 StreamingLLM Mistral-7B B=8 L=32768 cap=1024 (eager)", med, best, B * L, 4 * B * Hq * cap * d * 2)
+    med, best = timed_graph(lambda: cl.update_kv(K, Q, V, None, 4))
+    emit("cfg3 StreamingLLM Mistral-7B B=8 L=32768 cap=1024 (CUDA graph)", med, best, B * L, 4 * B * Hq * cap * d * 2)
     cl = H2OKVCluster(w, cap, 7, "avgpool")
     med, best = timed(lambda: cl.update_kv(K, Q, V, None, 4), iters=2, warm=1)
     emit("cfg3 H2O Mistral-7B B=8 L=32768 cap=1024 (all-query scores, two tcgen05 passes)", med, best, B * L,
@@ -88,8 +111,11 @@ def cfg4():
     state = rand(Hq, d, seed=9)
     head_lens, cu = cl.head_lens.clone(), cl.cu_klen.clone()
     med, best = timed(lambda: _native.update_flatten_view(flatK, state, head_lens, cu), iters=20)
-    emit("cfg4 AdaKV decode update_flatten_view (one tensor, one layer-step)", med, best, 1,
-         2 * (flatK.shape[0] * 2 + Hq) * d * 2 // 2)
+    emit("cfg4 AdaKV decode update_flatten_view (one tensor, one layer-step, eager)", med, best, 1,
+         (flatK.shape[0] * 2 + Hq) * d * 2)
+    med, best = timed_graph(lambda: _native.update_flatten_view(flatK, state, head_lens, cu))
+    emit("cfg4 AdaKV decode update_flatten_view (one tensor, one layer-step, CUDA graph)", med, best, 1,
+         (flatK.shape[0] * 2 + Hq) * d * 2)
 
 
 def cfg5():
@@ -109,7 +135,12 @@ def cfg5():
         med, best = timed(run, iters=12, warm=3)
         C = res["o"][0].shape[2]
         alg = Hkv * L * d * 2 + Hq * w * d * 2 + 4 * Hq * C * d * 2
-        emit(f"cfg5 PyramidKV 70B shard (1 KV head / 8 q heads) L=131072 layer {layer} kept {C}", med, best, L, alg)
+        emit(f"cfg5 PyramidKV 70B shard (1 KV head / 8 q heads) L=131072 layer {layer} kept {C} (eager)", med, best, L, alg)
+        def run_g():
+            i = it[0] % 6; it[0] += 1
+            return cl.update_kv_window(Ks[i], Qw, Vs[i], 8, L)
+        med, best = timed_graph(run_g, inner=12)
+        emit(f"cfg5 PyramidKV 70B shard (1 KV head / 8 q heads) L=131072 layer {layer} kept {C} (CUDA graph)", med, best, L, alg)
 
 
 if __name__ == "__main__":
