@@ -61,8 +61,15 @@ class HostCompressor:
                 dq.copy_(host_q_window[l], non_blocking=True)
                 ev_in[l].record(self.s_in)
             cur.wait_event(ev_in[l])
-            kc, vc = self.clusters[l].update_kv_window(dk, dq, host_v[l] if self.zero_copy_v else dv, self.groups,
-                                                       seq_len)
+            # select + gather stay on `cur` here: the staging buffers and the output copies are ordered by
+            # events on `cur`, and the step is PCIe-bound anyway (the tail is ~2 % of a layer's copy time)
+            tail_mode, self.clusters[l].async_tail = getattr(self.clusters[l], "async_tail", False), False
+            try:
+                kc, vc = self.clusters[l].update_kv_window(dk, dq, host_v[l] if self.zero_copy_v else dv, self.groups,
+                                                           seq_len)
+            finally:
+                self.clusters[l].async_tail = tail_mode
+
             esz = host_k[l].element_size()
             # bytes that cross PCIe towards the device: all of K, the query window, and either all of V or
             # only the V rows the gather kernel reads

@@ -101,8 +101,12 @@ def test_host_compressor_matches_device_path(zero_copy_v):
         Kc, Vc = dev_cl[l].update_kv(K.to(dev()), Q.to(dev()), V.to(dev()), None, 4)
         ref.append((Kc.cpu(), Vc.cpu()))
         hK.append(K.pin_memory()); hV.append(V.pin_memory()); hQ.append(Q[:, :, -w:].contiguous().pin_memory())
+    for c in host_cl:
+        c.async_tail = True            # as bench.py configures them: the host path must still order its copies
     hc = HostCompressor(host_cl, 4, dev(), zero_copy_v=zero_copy_v)
-    out = hc.run(hK, hQ, hV, shape.L)
+    hc.run(hK, hQ, hV, shape.L)
+    out = hc.run(hK, hQ, hV, shape.L)   # second run: staging buffers and pinned outputs are reused
+    assert all(c.async_tail for c in host_cl)
     torch.cuda.synchronize()
     for l in range(nl):
         assert torch.equal(out[l][0], ref[l][0]) and torch.equal(out[l][1], ref[l][1])
