@@ -184,6 +184,8 @@ class _ScoredCluster:
             if not torch.cuda.is_current_stream_capturing():
                 scores.record_stream(side)
                 idx.record_stream(gside)
+                for t in out:                  # allocated on the gather stream, consumed by the caller on `main`
+                    t.record_stream(main)
                 for t in (key_states, value_states):
                     if t.is_cuda:
                         t.record_stream(gside)
