@@ -375,6 +375,11 @@ window_score_fused_kernel(const __grid_constant__ CUtensorMap tmap_k, const Para
     // load of tile j+1 issued before the math of tile j into a second register buffer, and issued
     // between the convert and exp halves of tile j into the registers the convert half had just freed.)
     const uint32_t tcol = tmem_base + ((uint32_t)(quad * 32) << 16) + wg * 32;
+    // small windows (g*w < 128): the accumulator rows beyond g*w are zero padding -- warps that own only
+    // padding rows skip the load and the 32 exps per tile (w = 8 with 4 groups: 3 of 4 warps per warpgroup)
+    bool dead_rows[RB];
+#pragma unroll
+    for (int rb = 0; rb < RB; ++rb) dead_rows[rb] = __all_sync(0xffffffffu, (rb * 128 + r_loc) / W >= p.groups);
     int j = 0;
     for (; j < n1 * RB; ++j) {
       const int it = j / RB, rb = j % RB, buf = j % kNumBuf;
@@ -382,6 +387,11 @@ window_score_fused_kernel(const __grid_constant__ CUtensorMap tmap_k, const Para
       mbar_wait(tfull(buf), (j / kNumBuf) & 1);
       tc_fence_after();
       KVC_TILE_STAMP(et == 0, j, 4);
+      if (dead_rows[rb]) {  // all 32 rows of this warp are padding (g*w < 128): nothing to add up
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty(buf));
+        continue;
+      }
       uint32_t v[32];
       tmem_ld32(tcol + buf * 128, v);
       tmem_ld_wait();
@@ -501,6 +511,11 @@ window_score_fused_kernel(const __grid_constant__ CUtensorMap tmap_k, const Para
       mbar_wait(tfull(buf), (j / kNumBuf) & 1);
       tc_fence_after();
       KVC_TILE_STAMP(et == 0, j, 4);
+      if ((rb * 128 + wg * 32) / W >= p.groups) {  // this warpgroup's 32 columns are beyond the last head
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty(buf));
+        continue;
+      }
       uint32_t v[32];
       tmem_ld32(tcol + buf * 128, v);
       tmem_ld_wait();

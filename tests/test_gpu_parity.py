@@ -256,6 +256,8 @@ SCORE_CASES = [
     (1, 6, 3, 333, 64, 16),       # d = 64
     (1, 4, 2, 200, 128, 20),      # window not a multiple of 16
     (1, 32, 8, 4096, 128, 32),    # cfg-1 geometry
+    (1, 32, 8, 2048, 128, 8),     # LongBench driver default window 8: 32 of 128 accumulator rows are real
+    (1, 32, 8, 2048, 128, 16),    # 64 of 128 rows
 ]
 
 
