@@ -236,6 +236,7 @@ def run_ours(args, wl):
             cl = SnapKVCluster(w, wl["cap"], wl["kernel"], wl["pooling"])
         cl.score_impl = impl
         cl.async_tail = not args.sync_tail
+        cl.async_scores = not args.sync_tail and not args.sync_scores
         clusters.append(cl)
     groups = Hq // Hkv
 
@@ -403,7 +404,7 @@ def run_ours(args, wl):
             "scaling": "weak", "vs_baseline": None, "dtype": wl["dtype"], "data": "synthetic",
             "config": dict(config_of(args.workload, wl, world), score_impl=args.score_impl,
                            cuda_graph=graph is not None,
-                           async_tail=not args.sync_tail),
+                           async_tail=not args.sync_tail, async_scores=not args.sync_tail and not args.sync_scores),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
@@ -421,6 +422,7 @@ def main():
     ap.add_argument("--score-impl", default="auto", choices=["auto", "mma", "tc", "fused"])
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
     ap.add_argument("--sync-tail", action="store_true", help="keep select+gather on the caller's stream")
+    ap.add_argument("--sync-scores", action="store_true", help="keep the scoring kernel on the caller's stream")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -560,6 +560,313 @@ window_score_fused_kernel(const __grid_constant__ CUtensorMap tmap_k, const Para
   }
 }
 
+// =====================================================================================================
+// Half-footprint variant: the same two passes in a CTA HALF the size (8 epilogue warps, 2 accumulator
+// buffers = 256 TMEM columns, 2 K stages, ~100 KB of shared memory, <= 96 registers) so that TWO CTAs --
+// of two different launches -- share an SM.  A single launch leaves ~9 us of every ~34 us idle on every SM
+// (prologue, grid-barrier skew, statistics fold, tail); with the scoring launches of consecutive layers on
+// two streams those gaps are filled by the other layer's CTA.  Warpgroup g owns columns [64g, 64g+64) of
+// every tile (two 32-column chunks).  The grid barrier lives in the caller's workspace (two launches are
+// in flight at once), zeroed by a memset node before the launch.  RB == 1 only.
+constexpr int kHEpiWarps = 8;
+constexpr int kHNumWG = 2;
+constexpr int kHEpiThreads = kHEpiWarps * 32;
+constexpr int kHThreads = 32 * (2 + kHEpiWarps);
+constexpr int kHNumBuf = 2;
+
+struct HalfSmem {
+  static constexpr int kStages = 2;
+  static constexpr int kQBytes = kTileBytes;
+  static constexpr int kKBytes = kStages * kTileBytes;
+  static constexpr int kBarOff = kQBytes + kKBytes;
+  static constexpr int kNumBars = 2 * kStages + 2 * kHNumBuf + 1;
+  static constexpr int kTmemPtrOff = kBarOff + kNumBars * 8;
+  static constexpr int kCrowOff = (kTmemPtrOff + 4 + 15) & ~15;   // float[128]
+  static constexpr int kXstatOff = kCrowOff + 128 * 4;            // float2[2][128]
+  static constexpr int kTotal = kXstatOff + 2 * 128 * 8;
+  static constexpr int kAlloc = kTotal + 1024;
+};
+
+__device__ __forceinline__ void hepi_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kHEpiThreads) : "memory"); }
+
+template <typename T, int W>
+__global__ void __launch_bounds__(kHThreads, 2)
+window_score_half_kernel(const __grid_constant__ CUtensorMap tmap_k, const Params p, unsigned* sync_count) {
+  using SM = HalfSmem;
+  constexpr int S = SM::kStages;
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  unsigned char* smem = smem_raw + (base - raw_addr);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int chunk = blockIdx.x, unit = blockIdx.y;
+  const int b = unit / p.Hkv, kvh = unit % p.Hkv;
+  const int nscore = p.L - p.w;
+  const int tile_begin = chunk * p.chunk_tiles;
+  const int n1 = max(0, min(tile_begin + p.chunk_tiles, (p.L + kTile - 1) / kTile) - tile_begin);
+  const int n2 = max(0, min(tile_begin + p.chunk_tiles, (nscore + kTile - 1) / kTile) - tile_begin);
+  const int nq = p.groups * p.w;
+  auto tile_of = [&](int it) { return it < n1 ? tile_begin + it : tile_begin + (n2 - 1 - (it - n1)); };
+
+  const uint32_t q_s = base, k_s = base + SM::kQBytes, bar_s = base + SM::kBarOff;
+  auto kfull = [&](int s) { return bar_s + 8u * s; };
+  auto kempty = [&](int s) { return bar_s + 8u * (S + s); };
+  auto tfull = [&](int i) { return bar_s + 8u * (2 * S + i); };
+  auto tempty = [&](int i) { return bar_s + 8u * (2 * S + kHNumBuf + i); };
+  const uint32_t qbar = bar_s + 8u * (2 * S + 2 * kHNumBuf);
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + SM::kTmemPtrOff);
+  float* crow = reinterpret_cast<float*>(smem + SM::kCrowOff);
+  float2* xstat = reinterpret_cast<float2*>(smem + SM::kXstatOff);
+
+  tl_start(p.tl);
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(kfull(s), 1); mbar_init(kempty(s), 1); }
+    for (int i = 0; i < kHNumBuf; ++i) { mbar_init(tfull(i), 1); mbar_init(tempty(i), kHEpiWarps); }
+    mbar_init(qbar, kHEpiThreads);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
+                 "r"(256u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    int s = 0, ph = 1;
+    for (int it = 0; it < n1 + n2; ++it) {
+      mbar_wait(kempty(s), ph);
+      if (elect_one()) {
+        mbar_expect_tx(kfull(s), kTileBytes);
+        const int key0 = tile_of(it) * kTile;
+        tma_load_4d(k_s + s * kTileBytes, &tmap_k, kfull(s), 0, key0, kvh, b);
+        tma_load_4d(k_s + s * kTileBytes + kHalfBytes, &tmap_k, kfull(s), 64, key0, kvh, b);
+      }
+      __syncwarp();
+      if (++s == S) { s = 0; ph ^= 1; }
+    }
+  } else if (warp == 1) {
+    const int fmt = T::kDtype == KVC_BF16 ? 1 : 0;
+    const uint32_t idesc1 = instr_desc(fmt, 128, 128), idesc2 = instr_desc(fmt, 128, nq);
+    mbar_wait(qbar, 0);
+    tc_fence_after();
+    const uint64_t qd0 = smem_desc(q_s);
+    int s = 0, ph = 0, buf = 0, bph = 1;
+    for (int it = 0; it < n1 + n2; ++it) {
+      const bool second = it >= n1;
+      const uint32_t idesc = second ? idesc2 : idesc1;
+      mbar_wait(tempty(buf), bph);
+      mbar_wait(kfull(s), ph);
+      tc_fence_after();
+      const uint64_t kd0 = smem_desc(k_s + s * kTileBytes);
+      const uint64_t ad0 = second ? kd0 : qd0, bd0 = second ? qd0 : kd0;
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < kD / 16; ++k) {
+          const uint64_t off = (uint64_t)(((k >> 2) * kHalfBytes + (k & 3) * 32) >> 4);
+          tc_mma(tmem_base + buf * 128, ad0 + off, bd0 + off, idesc, k > 0);
+        }
+        tc_commit(tfull(buf));
+        tc_commit(kempty(s));
+      }
+      __syncwarp();
+      if (++buf == kHNumBuf) { buf = 0; bph ^= 1; }
+      if (++s == S) { s = 0; ph ^= 1; }
+    }
+  } else {
+    const int et = tid - 64;
+    const int wg = (warp - 2) >> 2;
+    const int quad = warp & 3;
+    const int r_loc = quad * 32 + lane;
+    const float scale = p.scale;
+    // stage the Q block: canonical K-major SWIZZLE_128B layout
+#pragma unroll
+    for (int it = 0; it < 128 * 16 / kHEpiThreads; ++it) {
+      const int e = et + it * kHEpiThreads;
+      const int r = e >> 4, c16 = e & 15;
+      const int hl = r / W, i = r % W;
+      const bool ok = hl < p.groups;
+      const uint16_t* src = p.q + b * p.q_sb + (int64_t)(kvh * p.groups + (ok ? hl : 0)) * p.q_sh +
+                            (int64_t)(nscore + i) * p.q_sl + c16 * 8;
+      const uint32_t dst = q_s + (c16 >> 3) * kHalfBytes + r * 128 + (((c16 & 7) ^ (r & 7)) << 4);
+      const int sz = ok ? 16 : 0;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_arrive(qbar);
+
+    const uint32_t tcol = tmem_base + ((uint32_t)(quad * 32) << 16) + wg * 64;
+    const bool dead_rows = __all_sync(0xffffffffu, r_loc / W >= p.groups);
+    // ---------------- pass 1 ----------------
+    float m_run = -1e30f;
+    float2 zacc[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+    int j = 0;
+    for (; j < n1; ++j) {
+      const int buf = j % kHNumBuf;
+      const int key0 = tile_of(j) * kTile + wg * 64;
+      mbar_wait(tfull(buf), (j / kHNumBuf) & 1);
+      tc_fence_after();
+      if (dead_rows) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty(buf));
+        continue;
+      }
+      uint32_t va[32], vb[32];
+      tmem_ld32(tcol + buf * 128, va);
+      tmem_ld32(tcol + buf * 128 + 32, vb);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty(buf));
+      if (key0 + 64 > nscore) {
+        const int last_key = min(p.L - 1, r_loc / W < p.groups ? nscore + r_loc % W : p.L - 1);
+        p1_chunk<T, true>(va, scale, m_run, zacc, key0, last_key);
+        p1_chunk<T, true>(vb, scale, m_run, zacc, key0 + 32, last_key);
+      } else {
+        p1_chunk<T, false>(va, scale, m_run, zacc, 0, 0);
+        p1_chunk<T, false>(vb, scale, m_run, zacc, 0, 0);
+      }
+    }
+    // ---------------- publish, grid barrier, fold ----------------
+    {
+      const float2 z2 = __fadd2_rn(__fadd2_rn(zacc[0], zacc[1]), __fadd2_rn(zacc[2], zacc[3]));
+      xstat[wg * 128 + r_loc] = make_float2(m_run, z2.x + z2.y);
+    }
+    hepi_sync();
+    if (et < 128) {
+      const float2 a = xstat[et], c = xstat[128 + et];
+      const float mn = fmaxf(a.x, c.x);
+      const float z = a.y * fast_exp2((a.x - mn) * kLog2e) + c.y * fast_exp2((c.x - mn) * kLog2e);
+      p.stats[((int64_t)unit * p.nchunks + chunk) * 128 + et] = make_float2(mn, z);
+    }
+    __threadfence();
+    hepi_sync();
+    if (et == 0) {
+      const unsigned total = gridDim.x * gridDim.y;
+      atomicAdd(sync_count, 1u);
+      unsigned seen = 0;
+      for (unsigned spin = 0; seen < total; ++spin) {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(sync_count) : "memory");
+        if (seen < total) {
+          __nanosleep(64);
+          if (spin > (1u << 24)) {
+            printf("kvc scores_fused(half): grid barrier timed out (block %d,%d: %u of %u arrived)\n", blockIdx.x, blockIdx.y, seen, total);
+            __trap();
+          }
+        }
+      }
+    }
+    hepi_sync();
+    {
+      constexpr int kParts = kHEpiThreads / 128;
+      const int r = et % 128, q = et / 128;
+      const float2* st = p.stats + (int64_t)unit * p.nchunks * 128 + r;
+      float M = -1e30f, Z = 0.f;
+      for (int c0 = q; c0 < p.nchunks; c0 += 8 * kParts) {
+        float2 sv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          sv[u] = make_float2(-1e30f, 0.f);
+          if (c0 + u * kParts < p.nchunks) {
+            const float2* a = st + (int64_t)(c0 + u * kParts) * 128;
+            asm volatile("ld.global.cg.v2.f32 {%0, %1}, [%2];" : "=f"(sv[u].x), "=f"(sv[u].y) : "l"(a) : "memory");
+          }
+        }
+        float mx = M;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) mx = fmaxf(mx, sv[u].x);
+        Z *= fast_exp2((M - mx) * kLog2e);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) Z += sv[u].y * fast_exp2((sv[u].x - mx) * kLog2e);
+        M = mx;
+      }
+      xstat[q * 128 + r] = make_float2(M, Z);
+      hepi_sync();
+      if (et < 128) {
+        const float2 a = xstat[et], c = xstat[128 + et];
+        const float mx = fmaxf(a.x, c.x);
+        const float z = a.y * fast_exp2((a.x - mx) * kLog2e) + c.y * fast_exp2((c.x - mx) * kLog2e);
+        crow[et] = (et / W < p.groups) ? (-mx * kLog2e - log2f(z)) : -INFINITY;
+      }
+    }
+    hepi_sync();
+    // ---------------- pass 2 ----------------
+    constexpr int kHeadsPerChunk = 32 / W;
+    for (; j < n1 + n2; ++j) {
+      const int buf = j % kHNumBuf;
+      const int key = tile_of(j) * kTile + r_loc;
+      mbar_wait(tfull(buf), (j / kHNumBuf) & 1);
+      tc_fence_after();
+      if ((wg * 64) / W >= p.groups) {  // both chunks of this warpgroup lie beyond the last head
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty(buf));
+        continue;
+      }
+      uint32_t va[32], vb[32];
+      tmem_ld32(tcol + buf * 128, va);
+      tmem_ld32(tcol + buf * 128 + 32, vb);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty(buf));
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int col0 = wg * 64 + c * 32;
+        if (col0 / W >= p.groups) continue;
+        float2 acc[kHeadsPerChunk];
+#pragma unroll
+        for (int h = 0; h < kHeadsPerChunk; ++h) acc[h] = make_float2(0.f, 0.f);
+        p2_chunk<T, W>(c == 0 ? va : vb, scale, crow + col0, acc);
+        if (key < nscore) {
+#pragma unroll
+          for (int h = 0; h < kHeadsPerChunk; ++h) {
+            const int head = col0 / W + h;
+            if (head < p.groups) {
+              float sum = acc[h].x + acc[h].y;
+              if (p.reduce_mean) sum = sum / (float)p.w;
+              p.out[((int64_t)b * p.Hq + kvh * p.groups + head) * nscore + key] = T::round1(sum);
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tl_end(p.tl);
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+  }
+}
+
+template <typename T, int W>
+static int launch_half(const CUtensorMap& tmap, const Params& sp, int units, unsigned* sync_count, cudaStream_t stream) {
+  auto kern = window_score_half_kernel<T, W>;
+  const int smem = HalfSmem::kAlloc;
+  KVC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  KVC_CUDA_TRY(cudaMemsetAsync(sync_count, 0, sizeof(unsigned), stream));
+  kern<<<dim3(sp.nchunks, units), kHThreads, smem, stream>>>(tmap, sp, sync_count);
+  return launch_status("window_score_half_kernel");
+}
+
+template <typename T>
+static int dispatch_half(const CUtensorMap& tmap, const Params& sp, int units, unsigned* sync_count, cudaStream_t stream) {
+  switch (sp.w) {
+    case 8: return launch_half<T, 8>(tmap, sp, units, sync_count, stream);
+    case 16: return launch_half<T, 16>(tmap, sp, units, sync_count, stream);
+    default: return launch_half<T, 32>(tmap, sp, units, sync_count, stream);
+  }
+}
+
 struct Plan {
   int rb, chunk_tiles, nchunks;
   size_t stats_bytes;
@@ -660,7 +967,7 @@ size_t window_scores_fused_workspace_bytes(int B, int Hq, int Hkv, int L, int d,
 
 int window_scores_fused(const void* q, int64_t q_sb, int64_t q_sh, int64_t q_sl, const void* k, int64_t k_sb,
                         int64_t k_sh, int64_t k_sl, int B, int Hq, int Hkv, int L, int d, int w, int dtype, int reduce,
-                        void* out_scores, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+                        void* out_scores, void* workspace, size_t workspace_bytes, bool half, cudaStream_t stream) {
   using namespace tcf;
   KVC_REQUIRE(window_scores_fused_supported(B, Hq, Hkv, L, d, w), KVC_ERR_UNSUPPORTED,
               "fused tcgen05 scoring kernel does not cover this shape (Hq/Hkv=%d, w=%d, d=%d, units=%d)", Hq / Hkv, w, d,
@@ -696,6 +1003,12 @@ int window_scores_fused(const void* q, int64_t q_sb, int64_t q_sh, int64_t q_sl,
   sp.out = (uint16_t*)out_scores;
   sp.tl = KVC_TL_SLOT(0);
   const int units = B * Hkv;
+  if (half) {
+    KVC_REQUIRE(pl.rb == 1, KVC_ERR_UNSUPPORTED, "half-footprint tcgen05 scoring kernel does not cover this shape: (Hq/Hkv)*w = %d > 128", (Hq / Hkv) * w);
+    unsigned* sync_count = (unsigned*)((char*)workspace + pl.stats_bytes);
+    return dtype == KVC_BF16 ? dispatch_half<Bf16>(tmap, sp, units, sync_count, stream)
+                             : dispatch_half<Fp16>(tmap, sp, units, sync_count, stream);
+  }
   if (dtype == KVC_BF16)
     return pl.rb == 1 ? dispatch_w<Bf16, 1>(tmap, sp, units, stream) : dispatch_w<Bf16, 2>(tmap, sp, units, stream);
   return pl.rb == 1 ? dispatch_w<Fp16, 1>(tmap, sp, units, stream) : dispatch_w<Fp16, 2>(tmap, sp, units, stream);

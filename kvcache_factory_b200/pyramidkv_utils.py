@@ -50,7 +50,8 @@ def compression_stream(device, which: int = None) -> "torch.cuda.Stream":
         _tail_turn[index] = (which + 1) % NUM_TAIL_STREAMS
     key = (index, which)
     if key not in _side_streams:
-        _side_streams[key] = torch.cuda.Stream(device)
+        # scoring streams (which >= 100) get the high priority: their CTAs are placed before the tails'
+        _side_streams[key] = torch.cuda.Stream(device, priority=-1 if which >= 100 else 0)
     return _side_streams[key]
 
 
@@ -121,6 +122,7 @@ class _ScoredCluster:
     keep_debug = False          # tests set this to read back scores / indices
     score_impl = N.IMPL_AUTO    # tests/bench may pin KVC_IMPL_MMA_SYNC or KVC_IMPL_TCGEN05
     async_tail = False          # run select + gather on the side stream (see wait_for_compression)
+    async_scores = False        # with async_tail: also the scoring leaves the caller's stream (half-footprint kernel)
 
     def _configure(self, window_size, max_capacity_prompt, kernel_size, pooling, merge):
         self.window_size = window_size
@@ -159,10 +161,28 @@ class _ScoredCluster:
         _check_merge(self.merge)
         w = self.window_size
         Hq = query_states.shape[1]
+        score_stream = None
         if scorer == "window":
             if pooling not in ("avgpool", "maxpool"):
                 raise ValueError("Pooling method not supported")
-            scores = N.window_scores(query_states, key_states, w, "sum", self.score_impl, seq_len=seq_len)
+            if self.async_tail and self.async_scores and (Hq // key_states.shape[1]) * w <= 128 and w <= 32 \
+                    and key_states.shape[-1] == 128:
+                # fully asynchronous: the scoring goes to one of two rotating streams as the half-footprint
+                # kernel, so that the scoring launches of consecutive calls share every SM and fill each
+                # other's prologue / grid-barrier / tail gaps (29.4 vs 34.6 us per cfg-2 layer)
+                dev = key_states.device
+                main = torch.cuda.current_stream(dev)
+                turn = _tail_turn.get(("s", dev.index), 0)
+                _tail_turn[("s", dev.index)] = (turn + 1) % 2
+                score_stream = compression_stream(dev, 100 + turn)
+                score_stream.wait_stream(main)
+                with torch.cuda.stream(score_stream):
+                    scores = N.window_scores(query_states, key_states, w, "sum", N.IMPL_TCGEN05_HALF, seq_len=seq_len)
+                if not torch.cuda.is_current_stream_capturing():
+                    for t in (query_states, key_states):
+                        t.record_stream(score_stream)
+            else:
+                scores = N.window_scores(query_states, key_states, w, "sum", self.score_impl, seq_len=seq_len)
         elif scorer == "h2o":
             scores = N.h2o_scores(query_states, key_states, w)
         else:
@@ -170,7 +190,7 @@ class _ScoredCluster:
         if self.async_tail and scores is not None:
             dev = key_states.device
             main, side = torch.cuda.current_stream(dev), compression_stream(dev)
-            side.wait_stream(main)
+            side.wait_stream(score_stream if score_stream is not None else main)
             with torch.cuda.stream(side):
                 idx, pooled, _ = N.pool_topk(scores, self.kernel_size, pooling, n_keep, want_pooled=self.keep_debug)
             gside = side

@@ -30,7 +30,8 @@ SCORE_EXACT_FRAC = 0.90
 TIE_RTOL = {torch.bfloat16: 2.0 ** -5, torch.float16: 2.0 ** -8}
 
 IMPLS = [pytest.param(_native.IMPL_MMA_SYNC, id="mma_sync"), pytest.param(_native.IMPL_TCGEN05, id="tcgen05"),
-         pytest.param(_native.IMPL_TCGEN05_FUSED, id="tcgen05_fused")]
+         pytest.param(_native.IMPL_TCGEN05_FUSED, id="tcgen05_fused"),
+         pytest.param(_native.IMPL_TCGEN05_HALF, id="tcgen05_half")]
 
 
 def dev():
@@ -522,7 +523,8 @@ def test_pyramidkv_full_size_properties(impl):
         del Kr, Vr
 
 
-def test_async_tail_matches_synchronous_path():
+@pytest.mark.parametrize("async_scores", [False, True])
+def test_async_tail_matches_synchronous_path(async_scores):
     """async_tail: select and gather of each layer run on rotating side streams (selects of consecutive
     layers overlap); after wait_for_compression() the results are bit-identical to the synchronous path."""
     from kvcache_factory_b200 import wait_for_compression
@@ -535,6 +537,8 @@ def test_async_tail_matches_synchronous_path():
         ins.append((Kd, Qd, Vd))
         cl = PyramidKVCluster(num_hidden_layers=nl, window_size=w, max_capacity_prompt=cap, kernel_size=7,
                               pooling="avgpool", layer_idx=l)
+        if async_scores:
+            cl.score_impl = _native.IMPL_TCGEN05_HALF   # same kernel as the asynchronous path: bit-comparable
         ref.append(cl.update_kv(Kd, Qd, Vd, None, 4))
     torch.cuda.synchronize()
     outs = []
@@ -544,6 +548,7 @@ def test_async_tail_matches_synchronous_path():
             cl = PyramidKVCluster(num_hidden_layers=nl, window_size=w, max_capacity_prompt=cap, kernel_size=7,
                                   pooling="avgpool", layer_idx=l)
             cl.async_tail = True
+            cl.async_scores = async_scores     # scoring too leaves the caller's stream (half-footprint kernel, 2 streams)
             outs.append(cl.update_kv(*ins[l], None, 4))
         wait_for_compression(dev())
         torch.cuda.current_stream().synchronize()
