@@ -16,6 +16,7 @@
 #include <cuda.h>
 
 #include <cstdlib>
+#include <mutex>
 
 #include "common.cuh"
 
@@ -566,8 +567,8 @@ window_score_fused_kernel(const __grid_constant__ CUtensorMap tmap_k, const Para
 // of two different launches -- share an SM.  A single launch leaves ~9 us of every ~34 us idle on every SM
 // (prologue, grid-barrier skew, statistics fold, tail); with the scoring launches of consecutive layers on
 // two streams those gaps are filled by the other layer's CTA.  Warpgroup g owns columns [64g, 64g+64) of
-// every tile (two 32-column chunks).  The grid barrier lives in the caller's workspace (two launches are
-// in flight at once), zeroed by a memset node before the launch.  RB == 1 only.
+// every tile (two 32-column chunks).  Two launches are in flight at once, so the grid barrier uses one
+// pair of library-owned, self-resetting words per STREAM.  RB == 1 only.
 constexpr int kHEpiWarps = 8;
 constexpr int kHNumWG = 2;
 constexpr int kHEpiThreads = kHEpiWarps * 32;
@@ -587,11 +588,14 @@ struct HalfSmem {
   static constexpr int kAlloc = kTotal + 1024;
 };
 
+constexpr int kHSlots = 16;
+__device__ unsigned g_hbar_count[kHSlots], g_hbar_gen[kHSlots];   // zero at module load, self-resetting
+
 __device__ __forceinline__ void hepi_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kHEpiThreads) : "memory"); }
 
 template <typename T, int W>
 __global__ void __launch_bounds__(kHThreads, 2)
-window_score_half_kernel(const __grid_constant__ CUtensorMap tmap_k, const Params p, unsigned* sync_count) {
+window_score_half_kernel(const __grid_constant__ CUtensorMap tmap_k, const Params p, int slot) {
   using SM = HalfSmem;
   constexpr int S = SM::kStages;
   extern __shared__ unsigned char smem_raw[];
@@ -684,6 +688,8 @@ window_score_half_kernel(const __grid_constant__ CUtensorMap tmap_k, const Param
     const int quad = warp & 3;
     const int r_loc = quad * 32 + lane;
     const float scale = p.scale;
+    unsigned my_gen = 0;
+    if (et == 0) asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(my_gen) : "l"(&g_hbar_gen[slot]) : "memory");
     // stage the Q block: canonical K-major SWIZZLE_128B layout
 #pragma unroll
     for (int it = 0; it < 128 * 16 / kHEpiThreads; ++it) {
@@ -749,16 +755,24 @@ window_score_half_kernel(const __grid_constant__ CUtensorMap tmap_k, const Param
     __threadfence();
     hepi_sync();
     if (et == 0) {
+      // sense-reversing barrier on the library-owned words of this launch's slot (one slot per stream:
+      // launches of one stream are serialised, launches of different streams use different slots)
       const unsigned total = gridDim.x * gridDim.y;
-      atomicAdd(sync_count, 1u);
-      unsigned seen = 0;
-      for (unsigned spin = 0; seen < total; ++spin) {
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(sync_count) : "memory");
-        if (seen < total) {
-          __nanosleep(64);
-          if (spin > (1u << 24)) {
-            printf("kvc scores_fused(half): grid barrier timed out (block %d,%d: %u of %u arrived)\n", blockIdx.x, blockIdx.y, seen, total);
-            __trap();
+      const unsigned old = atomicAdd(&g_hbar_count[slot], 1u);
+      if (old == total - 1) {
+        g_hbar_count[slot] = 0u;
+        __threadfence();
+        atomicAdd(&g_hbar_gen[slot], 1u);
+      } else {
+        unsigned gen = my_gen;
+        for (unsigned spin = 0; gen == my_gen; ++spin) {
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(gen) : "l"(&g_hbar_gen[slot]) : "memory");
+          if (gen == my_gen) {
+            __nanosleep(32);
+            if (spin > (1u << 24)) {
+              printf("kvc scores_fused(half): grid barrier timed out (block %d,%d slot %d)\n", blockIdx.x, blockIdx.y, slot);
+              __trap();
+            }
           }
         }
       }
@@ -848,22 +862,44 @@ window_score_half_kernel(const __grid_constant__ CUtensorMap tmap_k, const Param
   }
 }
 
+// Barrier slot of a stream: launches on one stream never overlap, launches on different streams must not
+// share barrier words.  More than kHSlots distinct streams are refused.
+static int half_slot(cudaStream_t stream) {
+  static std::mutex mu;
+  static cudaStream_t seen[kHSlots];
+  static int n = 0;
+  std::lock_guard<std::mutex> lock(mu);
+  for (int i = 0; i < n; ++i)
+    if (seen[i] == stream) return i;
+  if (n == kHSlots) return -1;
+  seen[n] = stream;
+  return n++;
+}
+
 template <typename T, int W>
-static int launch_half(const CUtensorMap& tmap, const Params& sp, int units, unsigned* sync_count, cudaStream_t stream) {
+static int launch_half(const CUtensorMap& tmap, const Params& sp, int units, cudaStream_t stream) {
   auto kern = window_score_half_kernel<T, W>;
   const int smem = HalfSmem::kAlloc;
   KVC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  KVC_CUDA_TRY(cudaMemsetAsync(sync_count, 0, sizeof(unsigned), stream));
-  kern<<<dim3(sp.nchunks, units), kHThreads, smem, stream>>>(tmap, sp, sync_count);
+  const int slot = half_slot(stream);
+  KVC_REQUIRE(slot >= 0, KVC_ERR_UNSUPPORTED, "half-footprint tcgen05 scoring kernel: more than %d distinct streams", kHSlots);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(sp.nchunks, units);
+  cfg.blockDim = dim3(kHThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  // no programmatic dependent launch here: with two launches in flight a pre-launched successor of the same
+  // stream competes with the other stream's launch for the free CTA slot of each SM (measured: 1.49 vs 1.46 ms)
+  KVC_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, tmap, sp, slot));
   return launch_status("window_score_half_kernel");
 }
 
 template <typename T>
-static int dispatch_half(const CUtensorMap& tmap, const Params& sp, int units, unsigned* sync_count, cudaStream_t stream) {
+static int dispatch_half(const CUtensorMap& tmap, const Params& sp, int units, cudaStream_t stream) {
   switch (sp.w) {
-    case 8: return launch_half<T, 8>(tmap, sp, units, sync_count, stream);
-    case 16: return launch_half<T, 16>(tmap, sp, units, sync_count, stream);
-    default: return launch_half<T, 32>(tmap, sp, units, sync_count, stream);
+    case 8: return launch_half<T, 8>(tmap, sp, units, stream);
+    case 16: return launch_half<T, 16>(tmap, sp, units, stream);
+    default: return launch_half<T, 32>(tmap, sp, units, stream);
   }
 }
 
@@ -1005,9 +1041,7 @@ int window_scores_fused(const void* q, int64_t q_sb, int64_t q_sh, int64_t q_sl,
   const int units = B * Hkv;
   if (half) {
     KVC_REQUIRE(pl.rb == 1, KVC_ERR_UNSUPPORTED, "half-footprint tcgen05 scoring kernel does not cover this shape: (Hq/Hkv)*w = %d > 128", (Hq / Hkv) * w);
-    unsigned* sync_count = (unsigned*)((char*)workspace + pl.stats_bytes);
-    return dtype == KVC_BF16 ? dispatch_half<Bf16>(tmap, sp, units, sync_count, stream)
-                             : dispatch_half<Fp16>(tmap, sp, units, sync_count, stream);
+    return dtype == KVC_BF16 ? dispatch_half<Bf16>(tmap, sp, units, stream) : dispatch_half<Fp16>(tmap, sp, units, stream);
   }
   if (dtype == KVC_BF16)
     return pl.rb == 1 ? dispatch_w<Bf16, 1>(tmap, sp, units, stream) : dispatch_w<Bf16, 2>(tmap, sp, units, stream);

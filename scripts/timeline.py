@@ -17,6 +17,7 @@ for l in range(nl):
     Qs.append(torch.randn(1, 32, w, 128, generator=g, device=dev).to(torch.bfloat16))
     c = PyramidKVCluster(num_hidden_layers=32, window_size=w, max_capacity_prompt=2048, kernel_size=7, pooling="avgpool", layer_idx=l * (32 // nl))
     c.async_tail = not sync_tail
+    c.async_scores = not sync_tail and '--sync-scores' not in sys.argv
     cls.append(c)
 def step():
     for l in range(nl):
