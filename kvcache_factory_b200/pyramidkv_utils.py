@@ -38,6 +38,7 @@ _tail_turn = {}
 NUM_TAIL_STREAMS = int(os.environ.get("KVC_TAIL_STREAMS", "3"))
 # gathers on their own rotating streams (a stream's next select then never waits behind a gather): 1.66 -> 1.60 ms
 NUM_GATHER_STREAMS = int(os.environ.get("KVC_GATHER_STREAMS", "2"))
+NUM_SCORE_STREAMS = int(os.environ.get("KVC_SCORE_STREAMS", "4"))   # async_scores: two half-footprint launches share an SM; 2 -> 1.45, 4 -> 1.43 ms
 
 
 def compression_stream(device, which: int = None) -> "torch.cuda.Stream":
@@ -173,7 +174,7 @@ class _ScoredCluster:
                 dev = key_states.device
                 main = torch.cuda.current_stream(dev)
                 turn = _tail_turn.get(("s", dev.index), 0)
-                _tail_turn[("s", dev.index)] = (turn + 1) % 2
+                _tail_turn[("s", dev.index)] = (turn + 1) % NUM_SCORE_STREAMS
                 score_stream = compression_stream(dev, 100 + turn)
                 score_stream.wait_stream(main)
                 with torch.cuda.stream(score_stream):
