@@ -221,14 +221,21 @@ def run_ours(args, wl):
     # synthetic inputs, device resident; each rank draws its own shard of the N-request batch
     g = torch.Generator(device=dev)
     Ks, Vs, Qs, clusters = [], [], [], []
+    q_window_only = nl * B * L * Hq * d * 2 > (32 << 30)
+    need = 2 * nl * B * Hkv * L * d * 2 + (0 if q_window_only else nl * B * L * Hq * d * 2)
+    if need > 0.8 * torch.cuda.get_device_properties(dev).total_memory:
+        raise SystemExit(f"workload {args.workload} needs {need / 2**30:.0f} GiB of device-resident inputs per GPU: shard it over more GPUs")
     for layer in range(nl):
         g.manual_seed(1234 + layer + 1000 * rank)
         Ks.append(torch.randn(B, Hkv, L, d, generator=g, device=dev, dtype=torch.float32).to(dtype))
         Vs.append(torch.randn(B, Hkv, L, d, generator=g, device=dev, dtype=torch.float32).to(dtype))
         # query_states as HF hands it over: a [B,L,Hq,d] buffer viewed as [B,Hq,L,d]; only the window is read
-        qbuf = torch.zeros(B, L, Hq, d, device=dev, dtype=dtype)
-        qbuf[:, L - w:] = torch.randn(B, w, Hq, d, generator=g, device=dev, dtype=torch.float32).to(dtype)
-        Qs.append(qbuf.transpose(1, 2))
+        if q_window_only:   # 70B at 128K: 80 full-length query tensors would be 160 GiB; the path reads the window only
+            Qs.append(torch.randn(B, w, Hq, d, generator=g, device=dev, dtype=torch.float32).to(dtype).transpose(1, 2))
+        else:
+            qbuf = torch.zeros(B, L, Hq, d, device=dev, dtype=dtype)
+            qbuf[:, L - w:] = torch.randn(B, w, Hq, d, generator=g, device=dev, dtype=torch.float32).to(dtype)
+            Qs.append(qbuf.transpose(1, 2))
         if wl["method"] == "pyramidkv":
             cl = PyramidKVCluster(num_hidden_layers=nl, window_size=w, max_capacity_prompt=wl["cap"],
                                   kernel_size=wl["kernel"], pooling=wl["pooling"], layer_idx=layer)
@@ -245,7 +252,10 @@ def run_ours(args, wl):
     def step():
         out = None
         for layer in range(nl):
-            out = clusters[layer].update_kv(Ks[layer], Qs[layer], Vs[layer], None, groups)
+            if q_window_only:
+                out = clusters[layer].update_kv_window(Ks[layer], Qs[layer], Vs[layer], groups, L)
+            else:
+                out = clusters[layer].update_kv(Ks[layer], Qs[layer], Vs[layer], None, groups)
         wait_for_compression(dev)  # join the asynchronous select/gather tails: all work ends inside the step
         return out
 
@@ -330,24 +340,26 @@ def run_ours(args, wl):
     from kvcache_factory_b200 import pyramidkv_utils as _U
     use_half = clusters[0].async_scores and groups * w <= 128 and w <= 32 and d == 128
 
+    qkw = dict(seq_len=L) if q_window_only else {}
+
     def scores_phase():
         """The scoring launches exactly as the step issues them: with async_scores the half-footprint kernel on
         the rotating high-priority streams (two launches share every SM), else the full kernel on one stream."""
         if not use_half:
-            return [_native.window_scores(Qs[l], Ks[l], w, "sum", impl) for l in range(nl)]
+            return [_native.window_scores(Qs[l], Ks[l], w, "sum", impl, **qkw) for l in range(nl)]
         cur, outs, used = torch.cuda.current_stream(), [], []
         for l in range(nl):
             st = _U.compression_stream(dev, 100 + l % _U.NUM_SCORE_STREAMS)
             if st not in used:
                 st.wait_stream(cur); used.append(st)
             with torch.cuda.stream(st):
-                outs.append(_native.window_scores(Qs[l], Ks[l], w, "sum", _native.IMPL_TCGEN05_HALF))
+                outs.append(_native.window_scores(Qs[l], Ks[l], w, "sum", _native.IMPL_TCGEN05_HALF, **qkw))
         for st in used:
             cur.wait_stream(st)
         return outs
 
     g_sc, scs = phase_graph(scores_phase)
-    g_solo, _solo = phase_graph(lambda: [_native.window_scores(Qs[l], Ks[l], w, "sum", impl) for l in range(nl)])
+    g_solo, _solo = phase_graph(lambda: [_native.window_scores(Qs[l], Ks[l], w, "sum", impl, **qkw) for l in range(nl)])
     g_se, idxs = phase_graph(lambda: [_native.pool_topk(scs[l], wl["kernel"], wl["pooling"], keeps[l])[0]
                                       for l in range(nl)])
     g_ga, _outs = phase_graph(lambda: [_native.gather_dense(Ks[l], Vs[l], idxs[l], Hq, keeps[l], w) for l in range(nl)])
@@ -394,7 +406,7 @@ def run_ours(args, wl):
         hc = HostCompressor(clusters, groups, dev)
         hK = [k.cpu().pin_memory() for k in Ks]
         hV = [v.cpu().pin_memory() for v in Vs]
-        hQ = [q[:, :, L - w:, :].contiguous().cpu().pin_memory() for q in Qs]   # the only rows the path reads
+        hQ = [(q if q_window_only else q[:, :, L - w:, :]).contiguous().cpu().pin_memory() for q in Qs]   # the only rows the path reads
         hc.run(hK, hQ, hV, L)                                                 # warm-up (allocates pinned outputs)
         hc.run(hK, hQ, hV, L)
         barrier()
