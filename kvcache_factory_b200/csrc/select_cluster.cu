@@ -489,6 +489,8 @@ static int dispatch_e(const void* scores, int rows, int n, int kernel_size, int 
   // 16.5 us when alone.  With 3 CTAs per SM (40 registers) the spills cost more than the overlap gains.
   // KVC_SELECT_THREADS=1024 forces the one-CTA-per-SM variant.
   static const bool half = [] { const char* e = getenv("KVC_SELECT_THREADS"); return !(e && atoi(e) == 1024); }();
+  // (for longer rows the 8- and 16-CTA clusters of this variant were measured slower than 1024 x 16: 77 vs 69 us
+  // per cfg-5 shard layer)
   if (half && n > 16384 && n <= 32768 && k <= kMaxK / 2)
     return launch<T, 16, POOL, 512>(scores, rows, n, (n + 8191) / 8192, kernel_size, k, k_per_row, out_idx, idx_stride, out_pooled, out_sums, stream);
   // one CTA occupies a whole SM (1 024 threads): prefer the slice length that keeps rows * C within one wave

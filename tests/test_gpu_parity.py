@@ -202,7 +202,8 @@ def test_flatten_cache_decode_steps():
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("pooling,kernel", [("avgpool", 7), ("avgpool", 5), ("maxpool", 7), ("maxpool", 1), (None, 1)])
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
-@pytest.mark.parametrize("n,k", [(4064, 96), (1000, 1000), (333, 1), (20000, 3932), (70000, 9000)])
+@pytest.mark.parametrize("n,k", [(4064, 96), (1000, 1000), (333, 1), (20000, 3932), (70000, 9000), (131040, 3964),
+                                 (50000, 4096)])
 def test_pool_topk_matches_torch(pooling, kernel, dtype, n, k):
     g = torch.Generator().manual_seed(n + k)
     rows = 6
