@@ -866,14 +866,16 @@ window_score_half_kernel(const __grid_constant__ CUtensorMap tmap_k, const Param
 // share barrier words.  More than kHSlots distinct streams are refused.
 static int half_slot(cudaStream_t stream) {
   static std::mutex mu;
-  static cudaStream_t seen[kHSlots];
-  static int n = 0;
+  static cudaStream_t seen[64][kHSlots];   // the barrier words are device globals: one table per device
+  static int n[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -1;
   std::lock_guard<std::mutex> lock(mu);
-  for (int i = 0; i < n; ++i)
-    if (seen[i] == stream) return i;
-  if (n == kHSlots) return -1;
-  seen[n] = stream;
-  return n++;
+  for (int i = 0; i < n[dev]; ++i)
+    if (seen[dev][i] == stream) return i;
+  if (n[dev] == kHSlots) return -1;
+  seen[dev][n[dev]] = stream;
+  return n[dev]++;
 }
 
 template <typename T, int W>
@@ -882,7 +884,7 @@ static int launch_half(const CUtensorMap& tmap, const Params& sp, int units, cud
   const int smem = HalfSmem::kAlloc;
   KVC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int slot = half_slot(stream);
-  KVC_REQUIRE(slot >= 0, KVC_ERR_UNSUPPORTED, "half-footprint tcgen05 scoring kernel: more than %d distinct streams", kHSlots);
+  KVC_REQUIRE(slot >= 0, KVC_ERR_UNSUPPORTED, "half-footprint tcgen05 scoring kernel: more than %d distinct streams on this device", kHSlots);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(sp.nchunks, units);
   cfg.blockDim = dim3(kHThreads);

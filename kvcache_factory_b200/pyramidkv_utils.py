@@ -178,7 +178,12 @@ class _ScoredCluster:
                 score_stream = compression_stream(dev, 100 + turn)
                 score_stream.wait_stream(main)
                 with torch.cuda.stream(score_stream):
-                    scores = N.window_scores(query_states, key_states, w, "sum", N.IMPL_TCGEN05_HALF, seq_len=seq_len)
+                    try:
+                        scores = N.window_scores(query_states, key_states, w, "sum", N.IMPL_TCGEN05_HALF, seq_len=seq_len)
+                    except N.KvcError as e:       # shape outside the half kernel: the regular kernel, same stream
+                        if e.status != -2:
+                            raise
+                        scores = N.window_scores(query_states, key_states, w, "sum", self.score_impl, seq_len=seq_len)
                 if not torch.cuda.is_current_stream_capturing():
                     for t in (query_states, key_states):
                         t.record_stream(score_stream)
