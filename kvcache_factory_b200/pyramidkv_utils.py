@@ -52,7 +52,9 @@ def compression_stream(device, which: int = None) -> "torch.cuda.Stream":
     key = (index, which)
     if key not in _side_streams:
         # scoring streams (which >= 100) get the high priority: their CTAs are placed before the tails'
-        _side_streams[key] = torch.cuda.Stream(device, priority=-1 if which >= 100 else 0)
+        prio = int(os.environ.get("KVC_PRIO_SCORE", "-1")) if which >= 100 else (
+            int(os.environ.get("KVC_PRIO_SELECT", "0")) if which < NUM_TAIL_STREAMS else int(os.environ.get("KVC_PRIO_GATHER", "0")))
+        _side_streams[key] = torch.cuda.Stream(device, priority=prio)
     return _side_streams[key]
 
 
