@@ -13,11 +13,14 @@ torch.cuda.synchronize()
 a, b = ref.view(torch.int16), out.view(torch.int16)
 print(f"half vs fused: {100 * (a == b).float().mean().item():.3f}% bit-identical, max |ulp diff| {(a.int() - b.int()).abs().max().item()}")
 s0, s1 = torch.cuda.Stream(), torch.cuda.Stream()
-def build(impl, streams):
+def build(impl, streams, stagger_cycles=0):
     gr = torch.cuda.CUDAGraph(); cap = torch.cuda.Stream(); cap.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(cap):
         with torch.cuda.graph(gr, stream=cap):
             for st in streams: st.wait_stream(cap)
+            if stagger_cycles and len(streams) > 1:
+                with torch.cuda.stream(streams[1]):
+                    torch.cuda._sleep(stagger_cycles)     # second stream starts half a kernel later
             keep = []
             for i in range(N):
                 with torch.cuda.stream(streams[i % len(streams)]):
@@ -37,3 +40,7 @@ for name, impl, streams in (("fused, 1 stream", _native.IMPL_TCGEN05_FUSED, [s0]
                             ("half, 3 streams", _native.IMPL_TCGEN05_HALF, [s0, s1, torch.cuda.Stream()])):
     gr, keep = build(impl, streams)
     print(f"{name:18s} {t(gr):7.1f} us per layer")
+
+for cyc in (10000, 20000, 30000, 40000, 60000):
+    gr, keep = build(_native.IMPL_TCGEN05_HALF, [s0, s1], cyc)
+    print(f"half, 2 streams, second delayed by {cyc} cycles: {t(gr):7.1f} us per layer")

@@ -555,3 +555,31 @@ def test_async_tail_matches_synchronous_path(async_scores):
         torch.cuda.current_stream().synchronize()
         for l in range(nl):
             assert torch.equal(outs[l][0], ref[l][0]) and torch.equal(outs[l][1], ref[l][1]), f"layer {l} round {rep}"
+
+
+def test_scoring_implementations_agree_on_random_shapes():
+    """Every tcgen05 scoring kernel against the mma.sync kernel on ragged random shapes (chunk boundaries,
+    partial tiles, padded row blocks, small windows): same rounding points, so at most 1 ulp apart and
+    almost always identical."""
+    rng = np.random.default_rng(2024)
+    checked = 0
+    for trial in range(24):
+        B = int(rng.integers(1, 3)); Hkv = int(rng.choice([1, 2, 4])); g = int(rng.choice([1, 2, 4, 8]))
+        w = int(rng.choice([8, 16, 32])); L = int(rng.integers(w + 130, 3000))
+        dtype = torch.bfloat16 if trial % 3 else torch.float16
+        shape = Shape(B, Hkv * g, Hkv, L, 128)
+        Q, K, _ = make_qkv(shape, dtype, layer_idx=trial, dist="peaked", window=w, q_window_only=True)
+        Qd, Kd = Q.to(dev()), K.to(dev())
+        ref = _native.window_scores(Qd, Kd, w, "sum", _native.IMPL_MMA_SYNC, seq_len=L)
+        for impl in (_native.IMPL_TCGEN05, _native.IMPL_TCGEN05_FUSED, _native.IMPL_TCGEN05_HALF):
+            try:
+                out = _native.window_scores(Qd, Kd, w, "sum", impl, seq_len=L)
+            except _native.KvcError as e:
+                if e.status == -2:
+                    continue
+                raise
+            a, b = to_bits(ref.cpu()).astype(np.int64), to_bits(out.cpu()).astype(np.int64)
+            assert np.abs(a - b).max() <= 1, (trial, shape, w, impl)
+            assert (a == b).mean() > 0.99, (trial, shape, w, impl)
+            checked += 1
+    assert checked >= 40
