@@ -402,16 +402,17 @@ def test_cluster_errors_like_reference():
 # ------------------------------------------------------------------------------------------------
 # AdaKV
 # ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("impl", [pytest.param(_native.IMPL_AUTO, id="auto")] + IMPLS)
 @pytest.mark.parametrize("name", golden_cases("adakv"))
-def test_adakv_matches_reference_vectors(name):
+def test_adakv_matches_reference_vectors(name, impl):
     c, z, (Q, K, V) = load_golden(name)
     kn = c["knobs"]
     dtype = DTYPES[c["dtype"]]
     w, H, d = kn["window_size"], c["Hq"], c["d"]
     cl = AdaKVCluster(**kn)
     cl.keep_debug = True
-    cl.score_impl = _native.IMPL_MMA_SYNC
-    fk, fv = cl.update_kv(K.to(dev()), Q.to(dev()), V.to(dev()))
+    cl.score_impl = impl
+    fk, fv = _skip_if_unsupported(lambda: cl.update_kv(K.to(dev()), Q.to(dev()), V.to(dev())))
     torch.cuda.synchronize()
     # metadata contract (dtypes, shapes, internal consistency)
     for a in ("head_lens", "cu_klen", "cu_headlens", "cu_qlen", "cu_offset", "cu_head_offset", "layer_qlens"):
@@ -452,8 +453,9 @@ def test_adakv_matches_reference_vectors(name):
         assert torch.equal(fk[cu[h]:cu[h + 1]].cpu(), rows_k) and torch.equal(fv[cu[h]:cu[h + 1]].cpu(), rows_v)
 
 
+@pytest.mark.parametrize("impl", [pytest.param(_native.IMPL_AUTO, id="auto")] + IMPLS)
 @pytest.mark.parametrize("name", golden_cases("headkv"))
-def test_headkv_matches_reference_vectors(name):
+def test_headkv_matches_reference_vectors(name, impl):
     from kvcache_factory_b200 import HeadKVCluster
     c, z, (Q, K, V) = load_golden(name)
     kn = dict(c["knobs"])
@@ -461,7 +463,8 @@ def test_headkv_matches_reference_vectors(name):
     w, H = kn["window_size"], c["Hq"]
     cl = HeadKVCluster(**kn)
     cl.keep_debug = True
-    fk, fv = cl.update_kv(K.to(dev()), Q.to(dev()), V.to(dev()))
+    cl.score_impl = impl
+    fk, fv = _skip_if_unsupported(lambda: cl.update_kv(K.to(dev()), Q.to(dev()), V.to(dev())))
     torch.cuda.synchronize()
     # capacities are inputs here, so the metadata is exact
     for a in ("head_lens", "cu_klen", "cu_headlens", "cu_qlen", "cu_offset", "cu_head_offset", "layer_qlens"):
