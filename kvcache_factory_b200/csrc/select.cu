@@ -107,7 +107,7 @@ pool_topk_kernel(const uint16_t* __restrict__ scores, int n, int kernel_size, in
                  const int32_t* __restrict__ k_per_row, int32_t* __restrict__ out_idx, int64_t idx_stride,
                  uint16_t* __restrict__ out_pooled, float* __restrict__ out_sums,
                  uint16_t* __restrict__ keys_scratch, unsigned long long* __restrict__ sort_scratch,
-                 int64_t sort_scratch_stride) {
+                 int64_t sort_scratch_stride, int sort_smem_cap) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SelShared& sh = *reinterpret_cast<SelShared*>(smem_raw);
   unsigned long long* sort_smem = reinterpret_cast<unsigned long long*>(smem_raw + sizeof(SelShared));
@@ -116,7 +116,7 @@ pool_topk_kernel(const uint16_t* __restrict__ scores, int n, int kernel_size, in
   const int tid = threadIdx.x;
   const uint16_t* srow = scores + (int64_t)row * n;
   uint16_t* keys = keys_scratch + (int64_t)row * n;
-  int k = k_per_row ? k_per_row[row] : k_fixed;
+  int k = k_per_row ? min(k_per_row[row], k_fixed) : k_fixed;   // k_fixed is also the width of an out_idx row
   if (k > n) k = n;
   if (k < 0) k = 0;
   const int radius = kernel_size / 2;
@@ -183,7 +183,9 @@ pool_topk_kernel(const uint16_t* __restrict__ scores, int n, int kernel_size, in
   // ---- pass C: ordered compaction into the sort buffer ------------------------------------------
   int kpad = 1;
   while (kpad < k) kpad <<= 1;
-  unsigned long long* buf = (kpad <= kSortSmemMax) ? sort_smem : sort_scratch + (int64_t)row * sort_scratch_stride;
+  // per-row k (AdaKV): a row with a small k sorts in shared memory even when the launch's largest k needs the
+  // global scratch; the shared-memory sort area is sized by the host for min(kpad of the largest k, kSortSmemMax)
+  unsigned long long* buf = (kpad <= sort_smem_cap) ? sort_smem : sort_scratch + (int64_t)row * sort_scratch_stride;
   constexpr int kItems = 4;
   for (int base = 0; base < n; base += kSelThreads * kItems) {
     const int j0 = base + tid * kItems;
@@ -271,11 +273,13 @@ int pool_topk(const void* scores, int rows, int n, int dtype, int kernel_size, i
   const size_t keys_bytes = ((size_t)rows * n * 2 + 255) & ~(size_t)255;
   uint16_t* keys = (uint16_t*)workspace;
   unsigned long long* sort_scratch = kpad > kSortSmemMax ? (unsigned long long*)((char*)workspace + keys_bytes) : nullptr;
-  const size_t smem = sizeof(SelShared) + (size_t)(kpad > kSortSmemMax ? 0 : kpad) * 8;
+  const int sort_smem_cap = kpad > kSortSmemMax ? kSortSmemMax : kpad;
+  const size_t smem = sizeof(SelShared) + (size_t)sort_smem_cap * 8;
   auto kern = dtype == KVC_BF16 ? pool_topk_kernel<Bf16> : pool_topk_kernel<Fp16>;
   KVC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<rows, kSelThreads, smem, stream>>>((const uint16_t*)scores, n, kernel_size, pool, k, k_per_row, out_idx,
-                                            idx_stride, (uint16_t*)out_pooled, out_sums, keys, sort_scratch, kpad);
+                                            idx_stride, (uint16_t*)out_pooled, out_sums, keys, sort_scratch, kpad,
+                                            sort_smem_cap);
   return launch_status("pool_topk_kernel");
 }
 

@@ -169,7 +169,7 @@ topk_cluster_kernel(const uint16_t* __restrict__ scores, int n, int kernel_size,
   const uint32_t crank = cluster_rank(), csize = cluster_size();
   const int row = blockIdx.y;
   const uint16_t* srow = scores + (int64_t)row * n;
-  int k = k_per_row ? k_per_row[row] : k_fixed;
+  int k = k_per_row ? min(k_per_row[row], k_fixed) : k_fixed;   // k_fixed bounds the sort buffers and an out_idx row
   k = min(max(k, 0), n);
   const int radius = POOL == KVC_POOL_NONE ? 0 : kernel_size / 2;
   const int s0 = (int)crank * SL;
