@@ -19,7 +19,7 @@ LIB_PATH = os.path.join(_PKG_DIR, "libkvc_b200.so")
 KVC_BF16, KVC_FP16 = 0, 1
 POOL_NONE, POOL_AVG, POOL_MAX = 0, 1, 2
 REDUCE_SUM, REDUCE_MEAN = 0, 1
-IMPL_AUTO, IMPL_MMA_SYNC, IMPL_TCGEN05, IMPL_TCGEN05_FUSED, IMPL_TCGEN05_HALF = 0, 1, 2, 3, 4
+IMPL_AUTO, IMPL_MMA_SYNC, IMPL_TCGEN05, IMPL_TCGEN05_FUSED, IMPL_TCGEN05_HALF, IMPL_TCGEN05_DYN = 0, 1, 2, 3, 4, 5
 ABI_VERSION = 1
 
 _POOL = {None: POOL_NONE, "none": POOL_NONE, "avgpool": POOL_AVG, "maxpool": POOL_MAX}

@@ -23,6 +23,10 @@ int window_scores_mma(const void*, int64_t, int64_t, int64_t, const void*, int64
                       int, int, int, int, int, void*, void*, size_t, cudaStream_t);
 size_t window_scores_tc_workspace_bytes(int B, int Hq, int Hkv, int L, int d, int w);
 bool window_scores_tc_supported(int B, int Hq, int Hkv, int L, int d, int w);
+bool window_scores_dyn_supported(int B, int Hq, int Hkv, int L, int d, int w);
+size_t window_scores_dyn_workspace_bytes(int B, int Hq, int Hkv, int L, int d, int w);
+int window_scores_dyn(const void*, int64_t, int64_t, int64_t, const void*, int64_t, int64_t, int64_t, int, int, int,
+                      int, int, int, int, int, void*, void*, size_t, cudaStream_t);
 bool window_scores_fused_supported(int B, int Hq, int Hkv, int L, int d, int w);
 size_t window_scores_fused_workspace_bytes(int B, int Hq, int Hkv, int L, int d, int w);
 int window_scores_fused(const void*, int64_t, int64_t, int64_t, const void*, int64_t, int64_t, int64_t, int, int, int,
@@ -139,7 +143,9 @@ size_t kvc_window_scores_workspace_bytes(int B, int Hq, int Hkv, int L, int d, i
   size_t a = window_scores_mma_workspace_bytes(B, Hq, Hkv, L, d, w);
   size_t b = window_scores_tc_workspace_bytes(B, Hq, Hkv, L, d, w);
   size_t c = window_scores_fused_workspace_bytes(B, Hq, Hkv, L, d, w);
+  size_t e = window_scores_dyn_workspace_bytes(B, Hq, Hkv, L, d, w);
   if (b > a) a = b;
+  if (e > a) a = e;
   return a > c ? a : c;
 }
 
@@ -150,16 +156,26 @@ int kvc_window_scores(const void* q, int64_t q_sb, int64_t q_sh, int64_t q_sl, c
   if (int rc = check_shape(B, Hq, Hkv, L, d, w, dtype)) return rc;
   KVC_REQUIRE(q && k && out_scores && workspace, KVC_ERR_ARG, "null pointer argument");
   KVC_REQUIRE(reduce == KVC_REDUCE_SUM || reduce == KVC_REDUCE_MEAN, KVC_ERR_ARG, "bad reduce %d", reduce);
-  KVC_REQUIRE(impl >= KVC_IMPL_AUTO && impl <= KVC_IMPL_TCGEN05_HALF, KVC_ERR_ARG, "bad impl %d", impl);
+  KVC_REQUIRE(impl >= KVC_IMPL_AUTO && impl <= KVC_IMPL_TCGEN05_DYN, KVC_ERR_ARG, "bad impl %d", impl);
   const bool tc_ok = window_scores_tc_supported(B, Hq, Hkv, L, d, w);
   const bool fused_ok = tc_ok && window_scores_fused_supported(B, Hq, Hkv, L, d, w);
+  const bool dyn_ok = tc_ok && window_scores_dyn_supported(B, Hq, Hkv, L, d, w);
+  // query/key rows that are not 16-byte aligned: only the mma.sync kernel takes them (IMPL_AUTO falls through)
+  const bool aligned = ((q_sb | q_sh | q_sl | k_sb | k_sh | k_sl) & 7) == 0 &&
+                       ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k)) & 15) == 0;
+  if (impl == KVC_IMPL_TCGEN05_DYN && !dyn_ok)
+    return fail(KVC_ERR_UNSUPPORTED, "tcgen05 scoring kernel does not cover this shape (Hq/Hkv=%d, w=%d, d=%d, units=%d)",
+                Hq / Hkv, w, d, B * Hkv);
+  if (impl == KVC_IMPL_TCGEN05_DYN || (impl == KVC_IMPL_AUTO && dyn_ok && aligned))
+    return window_scores_dyn(q, q_sb, q_sh, q_sl, k, k_sb, k_sh, k_sl, B, Hq, Hkv, L, d, w, dtype, reduce, out_scores,
+                             workspace, workspace_bytes, (cudaStream_t)stream);
   if ((impl == KVC_IMPL_TCGEN05 && !tc_ok) || ((impl == KVC_IMPL_TCGEN05_FUSED || impl == KVC_IMPL_TCGEN05_HALF) && !fused_ok))
     return fail(KVC_ERR_UNSUPPORTED, "tcgen05 scoring kernel does not cover this shape (Hq/Hkv=%d, w=%d, d=%d)",
                 Hq / Hkv, w, d);
-  if (impl == KVC_IMPL_TCGEN05_FUSED || impl == KVC_IMPL_TCGEN05_HALF || (impl == KVC_IMPL_AUTO && fused_ok))
+  if (impl == KVC_IMPL_TCGEN05_FUSED || impl == KVC_IMPL_TCGEN05_HALF || (impl == KVC_IMPL_AUTO && fused_ok && aligned))
     return window_scores_fused(q, q_sb, q_sh, q_sl, k, k_sb, k_sh, k_sl, B, Hq, Hkv, L, d, w, dtype, reduce, out_scores,
                                workspace, workspace_bytes, impl == KVC_IMPL_TCGEN05_HALF, (cudaStream_t)stream);
-  if (impl == KVC_IMPL_TCGEN05 || (impl == KVC_IMPL_AUTO && tc_ok))
+  if (impl == KVC_IMPL_TCGEN05 || (impl == KVC_IMPL_AUTO && tc_ok && aligned))
     return window_scores_tc(q, q_sb, q_sh, q_sl, k, k_sb, k_sh, k_sl, B, Hq, Hkv, L, d, w, dtype, reduce, out_scores,
                             workspace, workspace_bytes, (cudaStream_t)stream);
   return window_scores_mma(q, q_sb, q_sh, q_sl, k, k_sb, k_sh, k_sl, B, Hq, Hkv, L, d, w, dtype, reduce, out_scores,

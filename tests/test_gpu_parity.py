@@ -31,7 +31,8 @@ TIE_RTOL = {torch.bfloat16: 2.0 ** -5, torch.float16: 2.0 ** -8}
 
 IMPLS = [pytest.param(_native.IMPL_MMA_SYNC, id="mma_sync"), pytest.param(_native.IMPL_TCGEN05, id="tcgen05"),
          pytest.param(_native.IMPL_TCGEN05_FUSED, id="tcgen05_fused"),
-         pytest.param(_native.IMPL_TCGEN05_HALF, id="tcgen05_half")]
+         pytest.param(_native.IMPL_TCGEN05_HALF, id="tcgen05_half"),
+         pytest.param(_native.IMPL_TCGEN05_DYN, id="tcgen05_dyn")]
 
 
 def dev():
@@ -574,7 +575,7 @@ def test_scoring_implementations_agree_on_random_shapes():
         Q, K, _ = make_qkv(shape, dtype, layer_idx=trial, dist="peaked", window=w, q_window_only=True)
         Qd, Kd = Q.to(dev()), K.to(dev())
         ref = _native.window_scores(Qd, Kd, w, "sum", _native.IMPL_MMA_SYNC, seq_len=L)
-        for impl in (_native.IMPL_TCGEN05, _native.IMPL_TCGEN05_FUSED, _native.IMPL_TCGEN05_HALF):
+        for impl in (_native.IMPL_TCGEN05, _native.IMPL_TCGEN05_FUSED, _native.IMPL_TCGEN05_HALF, _native.IMPL_TCGEN05_DYN):
             try:
                 out = _native.window_scores(Qd, Kd, w, "sum", impl, seq_len=L)
             except _native.KvcError as e:
@@ -585,4 +586,4 @@ def test_scoring_implementations_agree_on_random_shapes():
             assert np.abs(a - b).max() <= 1, (trial, shape, w, impl)
             assert (a == b).mean() > 0.99, (trial, shape, w, impl)
             checked += 1
-    assert checked >= 40
+    assert checked >= 55
