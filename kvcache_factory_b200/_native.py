@@ -14,7 +14,8 @@ from ctypes import c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_void_
 import torch
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "libkvc_b200.so")
+# KVC_LIB_PATH: developer override (e.g. the `make TRACE=1` build, libkvc_b200_trace.so)
+LIB_PATH = os.environ.get("KVC_LIB_PATH") or os.path.join(_PKG_DIR, "libkvc_b200.so")
 
 KVC_BF16, KVC_FP16 = 0, 1
 POOL_NONE, POOL_AVG, POOL_MAX = 0, 1, 2

@@ -1,0 +1,31 @@
+"""Per-CTA timeline of the dynamically scheduled scoring kernel (needs `make TRACE=1 -C kvcache_factory_b200/csrc`
+and KVC_LIB_PATH=kvcache_factory_b200/libkvc_b200_trace.so).  usage: trace_dyn.py [L] [Hq] [Hkv]"""
+import os, sys, ctypes, statistics
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from kvcache_factory_b200 import _native
+L = int(sys.argv[1]) if len(sys.argv) > 1 else 32768
+Hq = int(sys.argv[2]) if len(sys.argv) > 2 else 32
+Hkv = int(sys.argv[3]) if len(sys.argv) > 3 else 8
+dev = torch.device("cuda:0")
+Ks = [torch.randn(1, Hkv, L, 128, device=dev).to(torch.bfloat16) for _ in range(6)]
+Q = torch.randn(1, Hq, 32, 128, device=dev).to(torch.bfloat16)
+for i in range(8):
+    s = _native.window_scores(Q, Ks[i % 6], 32, "sum", _native.IMPL_TCGEN05_DYN, seq_len=L)
+torch.cuda.synchronize()
+raw = ctypes.CDLL(_native.LIB_PATH)
+n = 148
+buf = (ctypes.c_longlong * (n * 8))()
+raw.kvc_debug_dyn_trace(buf, n * 8)
+t = [list(buf[i * 8:(i + 1) * 8]) for i in range(n)]
+t0 = min(r[0] for r in t if r[0] > 0)
+names = ["Q staged", "first tile", "chunk 1 published", "chunk 2 published", "x folded", "y folded", "end"]
+print("stamp            min   median      max   (ns after the first CTA started)")
+for k, nm in enumerate(names):
+    v = [r[k] - t0 for r in t if r[k] > 0]
+    if v:
+        print(f"{nm:14s} {min(v):7d} {int(statistics.median(v)):8d} {max(v):8d}")
+n1 = [r[7] // 1000 for r in t]; n2 = [r[7] % 1000 for r in t]
+print("pass-1 tiles per CTA: min %d max %d sum %d;  pass-2: min %d max %d sum %d" % (min(n1), max(n1), sum(n1), min(n2), max(n2), sum(n2)))
+for c in (0, 1, 8, 70, 147):
+    print("cta", c, [(x - t0) if x > 1000 else x for x in t[c]])
