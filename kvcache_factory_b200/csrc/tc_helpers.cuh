@@ -77,6 +77,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // K-major, 128-byte swizzle, 8-row groups 1024 bytes apart
 __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr) {
@@ -181,6 +188,69 @@ __device__ __forceinline__ void p2_chunk(const uint32_t (&v)[32], float scale, c
       const float2 e0 = poly ? exp2_fma2(f) : make_float2(fast_exp2(f.x), fast_exp2(f.y));
       const float2 e = make_float2(T::rnd(e0.x), T::rnd(e0.y));
       acc[(2 * i) / W] = __fadd2_rn(acc[(2 * i) / W], e);
+    }
+  }
+}
+
+// ---- 16-column halves (scores_dyn.cu): the tcgen05.ld of one half is in flight while the other half is computed ----
+// Pass 1, 16 keys of this thread's query row; same math as p1_chunk (the lazy reference is checked per half).
+template <typename T, bool MASK, int POLY>
+__device__ __forceinline__ void p1_half(const uint32_t (&v)[16], float scale, float& m_ref, float2 (&zacc)[4], int key0,
+                                        int last_key) {
+  const float2 scale2 = make_float2(scale, scale);
+  const float2 l2e2 = make_float2(kLog2e, kLog2e);
+  uint32_t r2[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float2 f = __fmul2_rn(make_float2(T::rnd(__uint_as_float(v[2 * i])), T::rnd(__uint_as_float(v[2 * i + 1]))), scale2);
+    r2[i] = T::pack(f.x, f.y);
+  }
+  if (MASK) {  // half touches the w x w causal block or the ragged end
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int key = key0 + 2 * i;
+      if (key > last_key) r2[i] = (r2[i] & 0xffff0000u) | (T::kNegInfPair & 0xffffu);
+      if (key + 1 > last_key) r2[i] = (r2[i] & 0x0000ffffu) | (T::kNegInfPair & 0xffff0000u);
+    }
+  }
+  uint32_t pm = T::max2(T::max2(T::max2(r2[0], r2[1]), T::max2(r2[2], r2[3])), T::max2(T::max2(r2[4], r2[5]), T::max2(r2[6], r2[7])));
+  const float cm = fmaxf(T::lo(pm), T::hi(pm));
+  if (__any_sync(0xffffffffu, cm > m_ref + kTau)) {
+    const float m_new = cm > m_ref + kTau ? cm : m_ref;
+    const float sc = fast_exp2((m_ref - m_new) * kLog2e);
+    const float2 sc2 = make_float2(sc, sc);
+#pragma unroll
+    for (int a = 0; a < 4; ++a) zacc[a] = __fmul2_rn(zacc[a], sc2);
+    m_ref = m_new;
+  }
+  const float2 ml2 = make_float2(-m_ref * kLog2e, -m_ref * kLog2e);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float2 a = __ffma2_rn(make_float2(T::lo(r2[i]), T::hi(r2[i])), l2e2, ml2);
+    const bool poly = POLY > 0 && ((i * POLY) / 8 != ((i + 1) * POLY) / 8);
+    const float2 e = poly ? exp2_fma2(a) : make_float2(fast_exp2(a.x), fast_exp2(a.y));
+    zacc[i & 3] = __fadd2_rn(zacc[i & 3], e);
+  }
+}
+
+// Pass 2, 16 stacked query rows (columns col0 .. col0+15 of the warp's 32) of this thread's key; acc[] spans the 32.
+template <typename T, int W, int POLY>
+__device__ __forceinline__ void p2_half(const uint32_t (&v)[16], float scale, const float* cr, int col0,
+                                        float2 (&acc)[32 / W]) {
+  const float2 scale2 = make_float2(scale, scale);
+  const float2 l2e2 = make_float2(kLog2e, kLog2e);
+#pragma unroll
+  for (int q4 = 0; q4 < 4; ++q4) {
+    const float4 c4 = *reinterpret_cast<const float4*>(cr + q4 * 4);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int i = 2 * q4 + h;
+      float2 f = __fmul2_rn(make_float2(T::rnd(__uint_as_float(v[2 * i])), T::rnd(__uint_as_float(v[2 * i + 1]))), scale2);
+      f = __ffma2_rn(make_float2(T::rnd(f.x), T::rnd(f.y)), l2e2, h == 0 ? make_float2(c4.x, c4.y) : make_float2(c4.z, c4.w));
+      const bool poly = POLY > 0 && ((i * POLY) / 8 != ((i + 1) * POLY) / 8);
+      const float2 e0 = poly ? exp2_fma2(f) : make_float2(fast_exp2(f.x), fast_exp2(f.y));
+      const float2 e = make_float2(T::rnd(e0.x), T::rnd(e0.y));
+      acc[(col0 + 2 * i) / W] = __fadd2_rn(acc[(col0 + 2 * i) / W], e);
     }
   }
 }

@@ -29,3 +29,17 @@ n1 = [r[7] // 1000 for r in t]; n2 = [r[7] % 1000 for r in t]
 print("pass-1 tiles per CTA: min %d max %d sum %d;  pass-2: min %d max %d sum %d" % (min(n1), max(n1), sum(n1), min(n2), max(n2), sum(n2)))
 for c in (0, 1, 8, 70, 147):
     print("cta", c, [(x - t0) if x > 1000 else x for x in t[c]])
+
+tb = (ctypes.c_uint * (2 * 64 * 8))()
+raw.kvc_debug_dyn_tile_trace(tb)
+for ci, cta in enumerate((0, 70)):
+    base = tb[(ci * 64 + 0) * 8 + 0]
+    print(f"--- CTA {cta}: per tile, SM cycles after the first TMA issue: tma_issue | mma kfull_seen, tempty_seen | epi(warp 2) tfull_seen loaded done | code")
+    prev = 0
+    for j in range(40):
+        r = [tb[(ci * 64 + j) * 8 + k] for k in range(8)]
+        code = r[6]
+        kind = "stop" if code == 0xffffffff else ("P2" if code & (1 << 27) else "P1") + (".y" if code & (1 << 26) else ".x") + (" L" if code & (1 << 28) else "")
+        d = [((x - base) & 0xffffffff) for x in r[:6]]
+        print(f"  {j:2d}: {d[0]:7d} | {d[1]:7d} {d[2]:7d} | {d[3]:7d} {d[4]:7d} {d[5]:7d}  (+{d[5] - prev:5d}) wg3 done {(r[7] - base) & 0xffffffff:7d} {kind} tile {code & ((1 << 26) - 1)}")
+        prev = d[5]

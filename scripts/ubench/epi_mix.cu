@@ -75,6 +75,43 @@ __device__ __forceinline__ void p1_cur(const uint32_t (&v)[32], float scale, flo
   }
 }
 
+// round-1 math, but the exponentials are taken SPECULATIVELY with the current reference before the packed-max vote
+// resolves (the vote then only guards a rare redo): the max tree leaves the critical path, results are bit-identical
+template <int F, int DEG>
+__device__ __forceinline__ void p1_spec(const uint32_t (&v)[32], float scale, float& m_ref, float2 (&zacc)[4]) {
+  const float2 scale2 = make_float2(scale, scale), l2e2 = make_float2(kLog2e, kLog2e);
+  uint32_t r2[16];
+  float2 zs[4] = {zacc[0], zacc[1], zacc[2], zacc[3]};
+  const float2 ml2 = make_float2(-m_ref * kLog2e, -m_ref * kLog2e);
+  uint32_t pm = 0xff80ff80u;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float2 f = __fmul2_rn(make_float2(rnd(__uint_as_float(v[2 * i])), rnd(__uint_as_float(v[2 * i + 1]))), scale2);
+    r2[i] = pack(f.x, f.y);
+    pm = max2(pm, r2[i]);
+    const float2 a = __ffma2_rn(make_float2(lo(r2[i]), hi(r2[i])), l2e2, ml2);
+    const bool poly = F > 0 && ((i * F) / 16 != ((i + 1) * F) / 16);
+    const float2 e = poly ? exp2_poly2<DEG>(a) : make_float2(ex2(a.x), ex2(a.y));
+    zs[i & 3] = __fadd2_rn(zs[i & 3], e);
+  }
+  const float cm = fmaxf(lo(pm), hi(pm));
+  if (__any_sync(0xffffffffu, cm > m_ref + 6.f)) {   // rare: redo the chunk with the raised reference
+    const float m_new = cm > m_ref + 6.f ? cm : m_ref;
+    const float sc = ex2((m_ref - m_new) * kLog2e);
+#pragma unroll
+    for (int a = 0; a < 4; ++a) zs[a] = __fmul2_rn(zacc[a], make_float2(sc, sc));
+    m_ref = m_new;
+    const float2 ml = make_float2(-m_ref * kLog2e, -m_ref * kLog2e);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float2 a = __ffma2_rn(make_float2(lo(r2[i]), hi(r2[i])), l2e2, ml);
+      zs[i & 3] = __fadd2_rn(zs[i & 3], make_float2(ex2(a.x), ex2(a.y)));
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a) zacc[a] = zs[a];
+}
+
 // F pairs of 16 through the polynomial (spread evenly), the rest through MUFU
 template <int F, int DEG>
 __device__ __forceinline__ void p1_new(const uint32_t (&v)[32], float scale, float& m_ref, float2 (&zacc)[4]) {
@@ -164,13 +201,14 @@ __device__ __forceinline__ void p2_packed(const uint32_t (&v)[32], float scale, 
 }
 
 template <int MODE, int F, int DEG>
-__global__ void __launch_bounds__(512, 1) k(float* out, const uint32_t* in) {
+__global__ void __launch_bounds__(512, 1) k(float* out, const uint32_t* in, int nthr) {
   __shared__ float cr[64];
   extern __shared__ uint4 vsm[];   // [8][512] uint4: thread t reads vsm[j*512 + t], conflict-free 16-byte accesses
   if (threadIdx.x < 64) cr[threadIdx.x] = -3.f - 0.01f * threadIdx.x;
   for (int j = 0; j < 8; ++j) {
     const uint32_t* p = in + ((threadIdx.x * 32 + j * 4) & 4095);
     vsm[j * 512 + threadIdx.x] = make_uint4(p[0], p[1], p[2], p[3]);
+  (void)nthr;
   }
   __syncthreads();
   float m_ref = 2.f;
@@ -190,6 +228,7 @@ __global__ void __launch_bounds__(512, 1) k(float* out, const uint32_t* in) {
     if (MODE == 2) p2_new<F, DEG>(v, 0.0883883461f, crp, acc);
     if (MODE == 3) p1_packed<F, DEG>(v, 0.0883883461f, m_ref, zacc);
     if (MODE == 4) p2_packed<F, DEG>(v, 0.0883883461f, crp, acc);
+    if (MODE == 5) p1_spec<F, DEG>(v, 0.0883883461f, m_ref, zacc);
   }
   out[blockIdx.x * blockDim.x + threadIdx.x] = zacc[0].x + zacc[1].y + zacc[2].x + zacc[3].y + acc.x + acc.y + m_ref;
 }
@@ -200,21 +239,26 @@ void run(const char* name) {
   uint32_t h[4096];
   for (int i = 0; i < 4096; ++i) { float x = ((i * 2654435761u) >> 8) % 2000 * 0.02f - 20.f; h[i] = *reinterpret_cast<uint32_t*>(&x); }
   cudaMemcpy(in, h, sizeof(h), cudaMemcpyHostToDevice);
-  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   cudaFuncSetAttribute(k<MODE, F, DEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
-  k<MODE, F, DEG><<<148, 512, 65536>>>(d, in); cudaDeviceSynchronize();
-  cudaEventRecord(e0); k<MODE, F, DEG><<<148, 512, 65536>>>(d, in); cudaEventRecord(e1); cudaEventSynchronize(e1);
-  float ms; cudaEventElapsedTime(&ms, e0, e1);
-  // per SMSP: 4 warps x ITER chunks; cycles per chunk per SMSP = time * clk / (4 * ITER)
-  const double clk = 1.965e9;
-  // per SMSP: 4 warps x ITER chunks of 32 elements per thread -> 128 * ITER warp-wide element groups
-  const double per_elem = ms * 1e-3 * clk / (128.0 * ITER);
-  printf("%-36s %7.3f ms  %5.2f clk per element (warp-wide) per SMSP  -> %5.0f clk per 128x128 tile\n", name, ms, per_elem, per_elem * 128);
+  double res[2];
+  for (int w = 0; w < 2; ++w) {
+    const int thr = w == 0 ? 128 : 512;   // 1 or 4 warps per SM sub-partition
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    k<MODE, F, DEG><<<148, thr, 65536>>>(d, in, thr); cudaDeviceSynchronize();
+    cudaEventRecord(e0); k<MODE, F, DEG><<<148, thr, 65536>>>(d, in, thr); cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    res[w] = ms * 1e-3 * 1.965e9 / ITER;   // cycles per 32-element chunk of ONE warp
+  }
+  printf("%-36s 1 warp/SMSP: %5.0f clk per chunk (latency of a lone warp) | 4 warps/SMSP: %5.0f clk per chunk each = %5.0f clk per 128x128 tile\n",
+         name, res[0], res[1], res[1]);
   cudaFree(d); cudaFree(in);
 }
 
 int main() {
   run<0, 0, 4>("p1 round-1 (packed max, lazy ref)");
+  run<5, 0, 4>("p1 speculative exps, 0/16 poly");
+  run<5, 4, 5>("p1 speculative exps, 4/16 deg5");
+  run<5, 6, 5>("p1 speculative exps, 6/16 deg5");
   run<1, 0, 4>("p1 nomax, 0/16 poly");
   run<1, 4, 4>("p1 nomax, 4/16 poly deg4");
   run<1, 5, 4>("p1 nomax, 5/16 poly deg4");
