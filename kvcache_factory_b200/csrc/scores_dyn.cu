@@ -322,7 +322,6 @@ window_score_dyn_kernel(const __grid_constant__ CUtensorMap tmap_k, const Params
     // pass 2: this warpgroup's 32 columns (stacked query rows) may lie beyond the unit's last head
     const int head0_0 = (ublk_0 * 128 + wg * 32) / W, head0_1 = (ublk_1 * 128 + wg * 32) / W;
     constexpr int kHeadsPerChunk = 32 / W;
-    bool ready_0 = false, ready_1 = false;   // c_row of the visit seen in shared memory
     int n1_tiles = 0, n2_tiles = 0, npub = 0;
 
     // Per tile a warp reads its 32 accumulator columns in two tcgen05.ld of 16.  A warp alone needs ~380 cycles of
@@ -331,127 +330,142 @@ window_score_dyn_kernel(const __grid_constant__ CUtensorMap tmap_k, const Params
     // the pipes idle during every latency phase (1700-2050 cycles per tile against ~1080 of math;
     // scripts/trace_dyn.py, scripts/ubench/epi_mix.cu).  Here the load of one half is always in flight while the
     // other half is computed -- tcgen05.wait::ld covers exactly one outstanding load -- at no cost in registers.
-    // No CTA-wide barrier anywhere: partials are handed to the stats warps through mbarriers, c_row comes back the
-    // same way.
-    constexpr int kNotReady = -2;
-    auto peek = [&](unsigned t, bool block) -> int {   // ring entry of tile t once its accumulator is complete
-      const uint32_t bar = tfull(t % kNumBuf), par = (t / kNumBuf) & 1;
-      if (block) mbar_wait(bar, par);
-      else if (!mbar_try(bar, par)) return kNotReady;
-      tc_fence_after();
-      return ring[t % kRing].x;
-    };
+    // The kernel is as much issue-bound as MUFU-bound (ncu: ~60 % issue slots, 35 % XU), so the loop is specialised
+    // per segment (unit visit x pass): everything that depends on the segment is hoisted out of the per-tile code.
+    // No CTA-wide barrier anywhere: partials go to the stats warps through mbarriers, c_row comes back the same way.
+    constexpr int kSegMask = kVisitBit | kPassBit;
     auto wants_load = [&](int code) -> bool {
       if (code < 0) return false;
       const int v = (code & kVisitBit) ? 1 : 0;
       return (code & kPassBit) ? VSEL(head0, v) < p.groups : !VSEL(dead_rows, v);
     };
+    // ring entry of tile t once its accumulator is complete (blocking)
+    auto peek_wait = [&](unsigned t) -> int {
+      mbar_wait(tfull(t % kNumBuf), (t / kNumBuf) & 1);
+      tc_fence_after();
+      return ring[t % kRing].x;
+    };
 
     uint32_t va[16], vb[16];
     unsigned ts = 0;
-    int code = peek(0, true);
-    bool have = wants_load(code);
+    int code = peek_wait(0);
+    bool have = wants_load(code);      // first half of tile ts is being loaded into va
     DYN_STAMP(et == 0, 1);
     if (have) tmem_ld16(tcol, va);
-    for (;;) {
-      if (code < 0) break;
-      DYN_TSTAMP(et == 0, ts, 3);
-      DYN_TSTAMP(et == 0, ts, 6, (unsigned)code);
-      const int tile = code & kTileMask;
+
+    // One tile of the current segment: the first half is in flight in va.  Loads the second half under the math of the
+    // first, frees the accumulator, starts the first half of tile ts+1 under the math of the second.  `seg_have` is the
+    // segment's answer to wants_load; at a segment boundary the next tile's answer is computed the general way.
+#define KVC_NEXT_TILE(seg)                                                                              \
+      int ncode = -1;                                                                                   \
+      const bool early = mbar_try(tfull((ts + 1) % kNumBuf), ((ts + 1) / kNumBuf) & 1);                 \
+      bool nhave = false;                                                                               \
+      if (early) {                                                                                      \
+        tc_fence_after();                                                                               \
+        ncode = ring[(ts + 1) % kRing].x;                                                               \
+        nhave = ncode >= 0 && (((ncode & kSegMask) == (seg)) ? have : wants_load(ncode));               \
+        if (nhave) tmem_ld16(tcol + ((ts + 1) % kNumBuf) * 128, va);                                    \
+      }
+#define KVC_NEXT_TILE_LATE()                                                                            \
+      if (!early) {                                                                                     \
+        ncode = peek_wait(ts + 1);                                                                      \
+        nhave = wants_load(ncode);                                                                      \
+        if (nhave) tmem_ld16(tcol + ((ts + 1) % kNumBuf) * 128, va);                                    \
+      }                                                                                                 \
+      ++ts; code = ncode; have = nhave;
+
+    while (code >= 0) {
+      const int seg = code & kSegMask;
       const int v = (code & kVisitBit) ? 1 : 0;
-      const bool p2 = (code & kPassBit) != 0;
-      const uint32_t tbuf = tcol + (ts % kNumBuf) * 128;
-      float2 acc[kHeadsPerChunk];
+      if (!(code & kPassBit)) {
+        // ================= pass-1 segment: thread <-> query row, columns are keys =================
+        const int rg = VSEL(ublk, v) * 128 + r_loc;
+        const int last_key = min(p.L - 1, rg / W < p.groups ? nscore + rg % W : p.L - 1);
+        const int first_masked = nscore - 32 - wg * 32;          // tile * 128 > this: the warp's 32 keys need the mask
+        const int my_unit = VSEL(unit, v);
+        do {
+          DYN_TSTAMP(et == 0, ts, 3);
+          DYN_TSTAMP(et == 0, ts, 6, (unsigned)code);
+          const int key0 = (code & kTileMask) * kTile + wg * 32;
+          const bool masked = (code & kTileMask) * kTile > first_masked;
+          if (have) {
+            tmem_ld_wait();
+            tmem_ld16(tcol + (ts % kNumBuf) * 128 + 16, vb);
+            DYN_TSTAMP(et == 0, ts, 4);
+            if (masked) p1_half<T, true, POLY1>(va, scale, m_run, zacc, key0, last_key);
+            else p1_half<T, false, POLY1>(va, scale, m_run, zacc, 0, 0);
+            tmem_ld_wait();
+            tc_fence_before();
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty(ts % kNumBuf));   // both halves are in registers: the accumulator is free
+          KVC_NEXT_TILE(seg)
+          if (have) {
+            if (masked) p1_half<T, true, POLY1>(vb, scale, m_run, zacc, key0 + 16, last_key);
+            else p1_half<T, false, POLY1>(vb, scale, m_run, zacc, 0, 0);
+          }
+          ++n1_tiles;
+          DYN_TSTAMP(et == 0 && zacc[0].x >= 0.f, ts, 5);
+          if (code & kLastBit) {
+            // ---- end of a chunk: hand this warp's slice of the partial to the stats warps, start afresh ----
+            const int slot = npub & 1;
+            mbar_wait(pub_empty(slot), ((npub >> 1) & 1) ^ 1);
+            const float2 z2 = __fadd2_rn(__fadd2_rn(zacc[0], zacc[1]), __fadd2_rn(zacc[2], zacc[3]));
+            xstat[(slot * kNumWG + wg) * 128 + r_loc] = make_float2(m_run, z2.x + z2.y);
+            if (et == 0) { pubreq[slot].x = my_unit; pubreq[slot].y = ring[ts % kRing].y; }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(pub_full(slot));
+            m_run = -1e30f;
 #pragma unroll
-      for (int h = 0; h < kHeadsPerChunk; ++h) acc[h] = make_float2(0.f, 0.f);
-      if (p2 && !VSEL(ready, v)) {   // first pass-2 tile of the visit: c_row must be there (normally it has been for long)
-        mbar_wait(crow_ready(v), 0);
-        if (v) ready_1 = true; else ready_0 = true;
+            for (int a = 0; a < 4; ++a) zacc[a] = make_float2(0.f, 0.f);
+            DYN_STAMP(et == 0 && npub < 2, 2 + npub);
+            ++npub;
+          }
+          KVC_NEXT_TILE_LATE()
+        } while (code >= 0 && (code & kSegMask) == seg);
+      } else {
+        // ================= pass-2 segment: thread <-> key, columns are the stacked query rows =================
+        mbar_wait(crow_ready(v), 0);   // c_row of the unit (normally there for long: see the header)
         DYN_STAMP(et == 0, 4 + v);
-      }
-      // ---- first half: columns [0, 16) are in va; start the load of [16, 32) ----
-      if (have) {
-        tmem_ld_wait();
-        tmem_ld16(tbuf + 16, vb);
-        DYN_TSTAMP(et == 0, ts, 4);
-        if (!p2) {
-          const int key0 = tile * kTile + wg * 32;
-          if (key0 + 32 > nscore) {  // touches the w x w causal block or the ragged end
-            const int rg = VSEL(ublk, v) * 128 + r_loc;
-            const int last_key = min(p.L - 1, rg / W < p.groups ? nscore + rg % W : p.L - 1);
-            p1_half<T, true, POLY1>(va, scale, m_run, zacc, key0, last_key);
-          } else {
-            p1_half<T, false, POLY1>(va, scale, m_run, zacc, 0, 0);
-          }
-        } else {
-          p2_half<T, W, POLY2>(va, scale, crow + v * 128 + wg * 32, 0, acc);
-        }
-        tmem_ld_wait();
-        tc_fence_before();
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty(ts % kNumBuf));   // both halves are in registers: the accumulator is free
-      // ---- the next tile: start the load of its first half before the math of this tile's second half ----
-      int ncode = peek(ts + 1, false);
-      const bool early = ncode != kNotReady;
-      bool nhave = early && wants_load(ncode);
-      if (nhave) tmem_ld16(tcol + ((ts + 1) % kNumBuf) * 128, va);
-      // ---- second half ----
-      if (have) {
-        if (!p2) {
-          const int key0 = tile * kTile + wg * 32 + 16;
-          if (key0 + 16 > nscore) {
-            const int rg = VSEL(ublk, v) * 128 + r_loc;
-            const int last_key = min(p.L - 1, rg / W < p.groups ? nscore + rg % W : p.L - 1);
-            p1_half<T, true, POLY1>(vb, scale, m_run, zacc, key0, last_key);
-          } else {
-            p1_half<T, false, POLY1>(vb, scale, m_run, zacc, 0, 0);
-          }
-        } else {
-          p2_half<T, W, POLY2>(vb, scale, crow + v * 128 + wg * 32 + 16, 16, acc);
-          const int key = tile * kTile + r_loc;
-          if (key < nscore) {
+        const float* cr = crow + v * 128 + wg * 32;
+        const int head0 = VSEL(head0, v);
+        uint16_t* out0 = p.out + ((int64_t)VSEL(ub, v) * p.Hq + VSEL(ukvh, v) * p.groups + head0) * nscore + r_loc;
+        const float inv_w = p.reduce_mean ? 1.0f / (float)p.w : 1.0f;   // exact: w is a power of two
+        do {
+          DYN_TSTAMP(et == 0, ts, 3);
+          DYN_TSTAMP(et == 0, ts, 6, (unsigned)code);
+          const int tile = code & kTileMask;
+          float2 acc[kHeadsPerChunk];
 #pragma unroll
-            for (int h = 0; h < kHeadsPerChunk; ++h) {
-              const int head = VSEL(head0, v) + h;
-              if (head < p.groups) {
-                float sum = acc[h].x + acc[h].y;
-                if (p.reduce_mean) sum = sum / (float)p.w;
-                p.out[((int64_t)VSEL(ub, v) * p.Hq + VSEL(ukvh, v) * p.groups + head) * nscore + key] = T::round1(sum);
-              }
+          for (int h = 0; h < kHeadsPerChunk; ++h) acc[h] = make_float2(0.f, 0.f);
+          if (have) {
+            tmem_ld_wait();
+            tmem_ld16(tcol + (ts % kNumBuf) * 128 + 16, vb);
+            DYN_TSTAMP(et == 0, ts, 4);
+            p2_half<T, W, POLY2>(va, scale, cr, 0, acc);
+            tmem_ld_wait();
+            tc_fence_before();
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty(ts % kNumBuf));
+          KVC_NEXT_TILE(seg)
+          if (have) {
+            p2_half<T, W, POLY2>(vb, scale, cr + 16, 16, acc);
+            if (tile * kTile + r_loc < nscore) {
+#pragma unroll
+              for (int h = 0; h < kHeadsPerChunk; ++h)
+                if (head0 + h < p.groups)
+                  out0[(int64_t)h * nscore + tile * kTile] = T::round1((acc[h].x + acc[h].y) * inv_w);
             }
           }
-        }
+          ++n2_tiles;
+          DYN_TSTAMP(et == 0, ts, 5);
+          KVC_NEXT_TILE_LATE()
+        } while (code >= 0 && (code & kSegMask) == seg);
       }
-      if (!p2) {
-        ++n1_tiles;
-        DYN_TSTAMP(et == 0 && zacc[0].x >= 0.f, ts, 5);
-        if (code & kLastBit) {
-          // ---- end of a chunk: hand this warp's slice of the partial to the stats warps, start afresh ----
-          const int slot = npub & 1;
-          mbar_wait(pub_empty(slot), ((npub >> 1) & 1) ^ 1);
-          const float2 z2 = __fadd2_rn(__fadd2_rn(zacc[0], zacc[1]), __fadd2_rn(zacc[2], zacc[3]));
-          xstat[(slot * kNumWG + wg) * 128 + r_loc] = make_float2(m_run, z2.x + z2.y);
-          if (et == 0) { pubreq[slot].x = VSEL(unit, v); pubreq[slot].y = ring[ts % kRing].y; }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(pub_full(slot));
-          m_run = -1e30f;
-#pragma unroll
-          for (int a = 0; a < 4; ++a) zacc[a] = make_float2(0.f, 0.f);
-          DYN_STAMP(et == 0 && npub < 2, 2 + npub);
-          ++npub;
-        }
-      } else {
-        ++n2_tiles;
-        DYN_TSTAMP(et == 0, ts, 5);
-      }
-      if (!early) {
-        ncode = peek(ts + 1, true);
-        nhave = wants_load(ncode);
-        if (nhave) tmem_ld16(tcol + ((ts + 1) % kNumBuf) * 128, va);
-      }
-      ++ts; code = ncode; have = nhave;
     }
+#undef KVC_NEXT_TILE
+#undef KVC_NEXT_TILE_LATE
     DYN_STAMP(et == 0, 6);
     DYN_STAMP(et == 0, 7, (long long)(n1_tiles * 1000 + n2_tiles));
   } else {
