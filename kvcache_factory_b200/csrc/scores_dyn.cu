@@ -40,8 +40,7 @@ constexpr int kStages = 4;
 constexpr int kEpiWarps = 16;
 constexpr int kNumWG = kEpiWarps / 4;
 constexpr int kEpiThreads = kEpiWarps * 32;
-constexpr int kStatWarps = 2;              // fold / publish helpers (see the kernel)
-constexpr int kThreads = 32 * (2 + kEpiWarps + kStatWarps);
+constexpr int kThreads = 32 * (2 + kEpiWarps);
 constexpr int kRing = 16;                 // > K stages + accumulator buffers: an entry is never overwritten while unread
 constexpr int kC2 = 2;                    // pass-2 tiles per claim
 
@@ -68,7 +67,6 @@ struct Params {
   int max_chunks;       // partial slots per unit in `stats`
   float scale;
   int reduce_mean;
-  int stagger;          // cycles between the warpgroups' starts (see the epilogue)
   float2* stats;        // [units][max_chunks][128]
   uint16_t* out;        // [B,Hq,L-w]
   unsigned long long* tl;
@@ -78,14 +76,12 @@ struct Smem {
   static constexpr int kQBytes = 2 * kTileBytes;                       // the Q blocks of the two units
   static constexpr int kKBytes = kStages * kTileBytes;
   static constexpr int kBarOff = kQBytes + kKBytes;
-  // K full/empty, accumulator full/empty, Q staged, publish full/empty x2, c_row ready x2
-  static constexpr int kNumBars = 2 * kStages + 2 * kNumBuf + 1 + 4 + 2;
+  static constexpr int kNumBars = 2 * kStages + 2 * kNumBuf + 1;
   static constexpr int kTmemPtrOff = kBarOff + kNumBars * 8;
   static constexpr int kRingOff = (kTmemPtrOff + 8 + 15) & ~15;        // int2[kRing]
-  static constexpr int kPubReqOff = kRingOff + kRing * 8;              // int2[2]: (unit, chunk) of a publish request
-  static constexpr int kCrowOff = kPubReqOff + 16;                     // float[2][128]
-  static constexpr int kXstatOff = kCrowOff + 2 * 128 * 4;             // float2[2][kNumWG][128]
-  static constexpr int kTotal = kXstatOff + 2 * kNumWG * 128 * 8;
+  static constexpr int kCrowOff = kRingOff + kRing * 8;                // float[2][128]
+  static constexpr int kXstatOff = kCrowOff + 2 * 128 * 4;             // float2[kNumWG][128]
+  static constexpr int kTotal = kXstatOff + kNumWG * 128 * 8;
   static constexpr int kAlloc = kTotal + 1024;
 };
 
@@ -99,18 +95,11 @@ __device__ __forceinline__ void dstamp(int slot, long long v = -1) {
   g_dtrace[blockIdx.x * 8 + slot] = v >= 0 ? v : t;
 }
 #define DYN_STAMP(cond, ...) do { if (cond) dstamp(__VA_ARGS__); } while (0)
-// per tile (first 64 of CTAs 0 and 70): SM-clock stamps {tma issue, mma: kfull seen, mma: tempty seen / issued,
-// epilogue warp 2: tfull seen, loaded, math done, code, epilogue warp 14 (warpgroup 3): math done}
-__device__ unsigned g_ttrace[2][64][8];
-__device__ __forceinline__ void tstamp(unsigned ts, int slot, unsigned v = 0xffffffffu) {
-  const int c = blockIdx.x == 0 ? 0 : blockIdx.x == 70 ? 1 : -1;
-  if (c >= 0 && ts < 64) g_ttrace[c][ts][slot] = v != 0xffffffffu ? v : (unsigned)clock64();
-}
-#define DYN_TSTAMP(cond, ...) do { if (cond) tstamp(__VA_ARGS__); } while (0)
 #else
 #define DYN_STAMP(cond, ...) do { } while (0)
-#define DYN_TSTAMP(cond, ...) do { } while (0)
 #endif
+
+__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
 
 // CTAs of a grid of G that serve unit u (u < nx: c % nx == u; else c % ny == u - nx), and the chunking of its tiles.
 __device__ __host__ __forceinline__ int serving_ctas(int u, int nx, int ny, int G) {
@@ -151,12 +140,8 @@ window_score_dyn_kernel(const __grid_constant__ CUtensorMap tmap_k, const Params
   auto tfull = [&](int i) { return bar_s + 8u * (2 * S + i); };
   auto tempty = [&](int i) { return bar_s + 8u * (2 * S + kNumBuf + i); };
   const uint32_t qbar = bar_s + 8u * (2 * S + 2 * kNumBuf);
-  auto pub_full = [&](int i) { return qbar + 8u * (1 + i); };     // 16 epilogue warps wrote their slice of a partial
-  auto pub_empty = [&](int i) { return qbar + 8u * (3 + i); };    // the stats warps have consumed it
-  auto crow_ready = [&](int v) { return qbar + 8u * (5 + v); };   // c_row of visit v is in shared memory
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + SM::kTmemPtrOff);
   volatile int2* ring = reinterpret_cast<volatile int2*>(smem + SM::kRingOff);
-  volatile int2* pubreq = reinterpret_cast<volatile int2*>(smem + SM::kPubReqOff);
   float* crow = reinterpret_cast<float*>(smem + SM::kCrowOff);
   float2* xstat = reinterpret_cast<float2*>(smem + SM::kXstatOff);
 
@@ -165,7 +150,6 @@ window_score_dyn_kernel(const __grid_constant__ CUtensorMap tmap_k, const Params
     for (int s = 0; s < S; ++s) { mbar_init(kfull(s), 1); mbar_init(kempty(s), 1); }
     for (int i = 0; i < kNumBuf; ++i) { mbar_init(tfull(i), 1); mbar_init(tempty(i), kEpiWarps); }
     mbar_init(qbar, kEpiThreads);
-    for (int i = 0; i < 2; ++i) { mbar_init(pub_full(i), kEpiWarps); mbar_init(pub_empty(i), kStatWarps); mbar_init(crow_ready(i), kStatWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -193,7 +177,6 @@ window_score_dyn_kernel(const __grid_constant__ CUtensorMap tmap_k, const Params
       if (elect_one()) {
         ring[ts % kRing].y = chunk;
         ring[ts % kRing].x = tile | (v ? kVisitBit : 0) | (pass ? kPassBit : 0) | (last ? kLastBit : 0);
-        DYN_TSTAMP(true, ts, 0);
         mbar_expect_tx(kfull(s), kTileBytes);
         tma_load_4d(k_s + s * kTileBytes, &tmap_k, kfull(s), 0, tile * kTile, VSEL(ukvh, v), VSEL(ub, v));
         tma_load_4d(k_s + s * kTileBytes + kHalfBytes, &tmap_k, kfull(s), 64, tile * kTile, VSEL(ukvh, v), VSEL(ub, v));
@@ -259,9 +242,7 @@ window_score_dyn_kernel(const __grid_constant__ CUtensorMap tmap_k, const Params
     for (int ts = 0;; ++ts) {
       mbar_wait(kfull(s), ph);
       const int code = ring[ts % kRing].x;
-      DYN_TSTAMP(lane == 0, ts, 1);
       mbar_wait(tempty(buf), bph);
-      DYN_TSTAMP(lane == 0, ts, 2);
       if (code < 0) {   // stop: hand the marker on to the epilogue through the next accumulator barrier
         if (elect_one()) mbar_arrive(tfull(buf));
         break;
@@ -285,7 +266,7 @@ window_score_dyn_kernel(const __grid_constant__ CUtensorMap tmap_k, const Params
       if (++buf == kNumBuf) { buf = 0; bph ^= 1; }
       if (++s == S) { s = 0; ph ^= 1; }
     }
-  } else if (warp < 2 + kEpiWarps) {
+  } else {
     // ===== epilogue warps: warpgroup g owns columns [32g, 32g+32) of every accumulator tile =====
     const int et = tid - 64;
     const int wg = (warp - 2) >> 2;
@@ -319,237 +300,156 @@ window_score_dyn_kernel(const __grid_constant__ CUtensorMap tmap_k, const Params
     // rows beyond the unit's last head are zero padding: warps that own only padding rows skip the load and the exps
     const bool dead_rows_0 = __all_sync(0xffffffffu, (ublk_0 * 128 + r_loc) / W >= p.groups);
     const bool dead_rows_1 = __all_sync(0xffffffffu, (ublk_1 * 128 + r_loc) / W >= p.groups);
-    // pass 2: this warpgroup's 32 columns (stacked query rows) may lie beyond the unit's last head
-    const int head0_0 = (ublk_0 * 128 + wg * 32) / W, head0_1 = (ublk_1 * 128 + wg * 32) / W;
     constexpr int kHeadsPerChunk = 32 / W;
+    bool folded_0 = false, folded_1 = false;
     int n1_tiles = 0, n2_tiles = 0, npub = 0;
 
-    // Per tile a warp reads its 32 accumulator columns in two tcgen05.ld of 16.  A warp alone needs ~380 cycles of
-    // math per 32 columns and ~700 of latency (mbarrier wait, tcgen05.ld); the four warps of an SM sub-partition share
-    // the TMEM lane quarter, are released by the same barriers and stay in lockstep, so with load -> math in sequence
-    // the pipes idle during every latency phase (1700-2050 cycles per tile against ~1080 of math;
-    // scripts/trace_dyn.py, scripts/ubench/epi_mix.cu).  Here the load of one half is always in flight while the
-    // other half is computed -- tcgen05.wait::ld covers exactly one outstanding load -- at no cost in registers.
-    // The kernel is as much issue-bound as MUFU-bound (ncu: ~60 % issue slots, 35 % XU), so the loop is specialised
-    // per segment (unit visit x pass): everything that depends on the segment is hoisted out of the per-tile code.
-    // No CTA-wide barrier anywhere: partials go to the stats warps through mbarriers, c_row comes back the same way.
-    constexpr int kSegMask = kVisitBit | kPassBit;
-    auto wants_load = [&](int code) -> bool {
-      if (code < 0) return false;
-      const int v = (code & kVisitBit) ? 1 : 0;
-      return (code & kPassBit) ? VSEL(head0, v) < p.groups : !VSEL(dead_rows, v);
-    };
-    // ring entry of tile t once its accumulator is complete (blocking)
-    auto peek_wait = [&](unsigned t) -> int {
-      mbar_wait(tfull(t % kNumBuf), (t / kNumBuf) & 1);
+    for (unsigned ts = 0;; ++ts) {
+      const int buf = ts % kNumBuf;
+      mbar_wait(tfull(buf), (ts / kNumBuf) & 1);
       tc_fence_after();
-      return ring[t % kRing].x;
-    };
-
-    uint32_t va[16], vb[16];
-    unsigned ts = 0;
-    int code = peek_wait(0);
-    bool have = wants_load(code);      // first half of tile ts is being loaded into va
-    DYN_STAMP(et == 0, 1);
-    if (have) tmem_ld16(tcol, va);
-
-    // One tile of the current segment: the first half is in flight in va.  Loads the second half under the math of the
-    // first, frees the accumulator, starts the first half of tile ts+1 under the math of the second.  `seg_have` is the
-    // segment's answer to wants_load; at a segment boundary the next tile's answer is computed the general way.
-#define KVC_NEXT_TILE(seg)                                                                              \
-      int ncode = -1;                                                                                   \
-      const bool early = mbar_try(tfull((ts + 1) % kNumBuf), ((ts + 1) / kNumBuf) & 1);                 \
-      bool nhave = false;                                                                               \
-      if (early) {                                                                                      \
-        tc_fence_after();                                                                               \
-        ncode = ring[(ts + 1) % kRing].x;                                                               \
-        nhave = ncode >= 0 && (((ncode & kSegMask) == (seg)) ? have : wants_load(ncode));               \
-        if (nhave) tmem_ld16(tcol + ((ts + 1) % kNumBuf) * 128, va);                                    \
-      }
-#define KVC_NEXT_TILE_LATE()                                                                            \
-      if (!early) {                                                                                     \
-        ncode = peek_wait(ts + 1);                                                                      \
-        nhave = wants_load(ncode);                                                                      \
-        if (nhave) tmem_ld16(tcol + ((ts + 1) % kNumBuf) * 128, va);                                    \
-      }                                                                                                 \
-      ++ts; code = ncode; have = nhave;
-
-    while (code >= 0) {
-      const int seg = code & kSegMask;
+      const int code = ring[ts % kRing].x;
+      DYN_STAMP(et == 0 && ts == 0, 1);
+      if (code < 0) break;
+      const int tile = code & kTileMask;
       const int v = (code & kVisitBit) ? 1 : 0;
       if (!(code & kPassBit)) {
-        // ================= pass-1 segment: thread <-> query row, columns are keys =================
-        const int rg = VSEL(ublk, v) * 128 + r_loc;
-        const int last_key = min(p.L - 1, rg / W < p.groups ? nscore + rg % W : p.L - 1);
-        const int first_masked = nscore - 32 - wg * 32;          // tile * 128 > this: the warp's 32 keys need the mask
-        const int my_unit = VSEL(unit, v);
-        do {
-          DYN_TSTAMP(et == 0, ts, 3);
-          DYN_TSTAMP(et == 0, ts, 6, (unsigned)code);
-          const int key0 = (code & kTileMask) * kTile + wg * 32;
-          const bool masked = (code & kTileMask) * kTile > first_masked;
-          if (have) {
-            tmem_ld_wait();
-            tmem_ld16(tcol + (ts % kNumBuf) * 128 + 16, vb);
-            DYN_TSTAMP(et == 0, ts, 4);
-            if (masked) p1_half<T, true, POLY1>(va, scale, m_run, zacc, key0, last_key);
-            else p1_half<T, false, POLY1>(va, scale, m_run, zacc, 0, 0);
-            tmem_ld_wait();
-            tc_fence_before();
-          }
+        // ---------------- pass 1: thread <-> query row, columns are keys ----------------
+        const int key0 = tile * kTile + wg * 32;
+        if (VSEL(dead_rows, v)) {
           __syncwarp();
-          if (lane == 0) mbar_arrive(tempty(ts % kNumBuf));   // both halves are in registers: the accumulator is free
-          KVC_NEXT_TILE(seg)
-          if (have) {
-            if (masked) p1_half<T, true, POLY1>(vb, scale, m_run, zacc, key0 + 16, last_key);
-            else p1_half<T, false, POLY1>(vb, scale, m_run, zacc, 0, 0);
+          if (lane == 0) mbar_arrive(tempty(buf));
+        } else {
+          uint32_t vals[32];
+          tmem_ld32(tcol + buf * 128, vals);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty(buf));
+          if (key0 + 32 > nscore) {  // chunk touches the w x w causal block or the ragged end
+            const int rg = VSEL(ublk, v) * 128 + r_loc;
+            const int last_key = min(p.L - 1, rg / W < p.groups ? nscore + rg % W : p.L - 1);
+            p1_chunk<T, true, POLY1>(vals, scale, m_run, zacc, key0, last_key);
+          } else {
+            p1_chunk<T, false, POLY1>(vals, scale, m_run, zacc, 0, 0);
           }
-          ++n1_tiles;
-          DYN_TSTAMP(et == 0 && zacc[0].x >= 0.f, ts, 5);
-          if (code & kLastBit) {
-            // ---- end of a chunk: hand this warp's slice of the partial to the stats warps, start afresh ----
-            const int slot = npub & 1;
-            mbar_wait(pub_empty(slot), ((npub >> 1) & 1) ^ 1);
-            const float2 z2 = __fadd2_rn(__fadd2_rn(zacc[0], zacc[1]), __fadd2_rn(zacc[2], zacc[3]));
-            xstat[(slot * kNumWG + wg) * 128 + r_loc] = make_float2(m_run, z2.x + z2.y);
-            if (et == 0) { pubreq[slot].x = my_unit; pubreq[slot].y = ring[ts % kRing].y; }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(pub_full(slot));
-            m_run = -1e30f;
+        }
+        ++n1_tiles;
+        if (code & kLastBit) {
+          // ---- end of a chunk: combine the four column slices (fixed order), publish the partial ----
+          const int chunk = ring[ts % kRing].y;
+          const float2 z2 = __fadd2_rn(__fadd2_rn(zacc[0], zacc[1]), __fadd2_rn(zacc[2], zacc[3]));
+          xstat[wg * 128 + r_loc] = make_float2(m_run, z2.x + z2.y);
+          epi_sync();
+          if (et < 128) {
+            float mn = -1e30f, z = 0.f;
 #pragma unroll
-            for (int a = 0; a < 4; ++a) zacc[a] = make_float2(0.f, 0.f);
-            DYN_STAMP(et == 0 && npub < 2, 2 + npub);
-            ++npub;
+            for (int g = 0; g < kNumWG; ++g) mn = fmaxf(mn, xstat[g * 128 + et].x);
+#pragma unroll
+            for (int g = 0; g < kNumWG; ++g) {
+              const float2 a = xstat[g * 128 + et];
+              z += a.y * fast_exp2((a.x - mn) * kLog2e);
+            }
+            p.stats[((int64_t)VSEL(unit, v) * p.max_chunks + chunk) * 128 + et] = make_float2(mn, z);
+            __threadfence();
           }
-          KVC_NEXT_TILE_LATE()
-        } while (code >= 0 && (code & kSegMask) == seg);
+          epi_sync();
+          if (et == 0) atomicAdd(&ctl->done[VSEL(unit, v)], 1u);
+          m_run = -1e30f;
+#pragma unroll
+          for (int a = 0; a < 4; ++a) zacc[a] = make_float2(0.f, 0.f);
+          DYN_STAMP(et == 0 && npub < 2, 2 + npub);
+          ++npub;
+        }
       } else {
-        // ================= pass-2 segment: thread <-> key, columns are the stacked query rows =================
-        mbar_wait(crow_ready(v), 0);   // c_row of the unit (normally there for long: see the header)
-        DYN_STAMP(et == 0, 4 + v);
-        const float* cr = crow + v * 128 + wg * 32;
-        const int head0 = VSEL(head0, v);
-        uint16_t* out0 = p.out + ((int64_t)VSEL(ub, v) * p.Hq + VSEL(ukvh, v) * p.groups + head0) * nscore + r_loc;
-        const float inv_w = p.reduce_mean ? 1.0f / (float)p.w : 1.0f;   // exact: w is a power of two
-        do {
-          DYN_TSTAMP(et == 0, ts, 3);
-          DYN_TSTAMP(et == 0, ts, 6, (unsigned)code);
-          const int tile = code & kTileMask;
+        // ---------------- pass 2: thread <-> key, columns are the stacked query rows ----------------
+        if (!VSEL(folded, v)) {
+          // Fold the unit's partials (chunk order) into c_row = -M log2e - log2 Z.  Every chunk of the unit was
+          // claimed by a RUNNING CTA before any pass-2 tile of it could be claimed, and those CTAs publish without
+          // waiting for anybody: this wait always ends (normally it does not wait at all, see the header).
+          if (v) folded_1 = true; else folded_0 = true;
+          if (et == 0) {
+            for (unsigned spin = 0; ld_acquire_u32(&ctl->done[VSEL(unit, v)]) < (unsigned)VSEL(n1c, v); ++spin) {
+              __nanosleep(40);
+              if (spin > (1u << 24)) {
+                printf("kvc scores_dyn: statistics of unit %d never completed (block %d)\n", VSEL(unit, v), blockIdx.x);
+                __trap();
+              }
+            }
+          }
+          epi_sync();
+          const int nparts = VSEL(n1c, v);
+          constexpr int kParts = kEpiThreads / 128;
+          const int r = et % 128, q = et / 128;
+          const float2* st = p.stats + (int64_t)VSEL(unit, v) * p.max_chunks * 128 + r;
+          float M = -1e30f, Z = 0.f;
+          for (int c0 = q; c0 < nparts; c0 += 8 * kParts) {
+            float2 sv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              sv[u] = make_float2(-1e30f, 0.f);
+              if (c0 + u * kParts < nparts) {
+                const float2* a = st + (int64_t)(c0 + u * kParts) * 128;
+                asm volatile("ld.global.cg.v2.f32 {%0, %1}, [%2];" : "=f"(sv[u].x), "=f"(sv[u].y) : "l"(a) : "memory");  // written by other SMs: bypass L1
+              }
+            }
+            float mx = M;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) mx = fmaxf(mx, sv[u].x);
+            Z *= fast_exp2((M - mx) * kLog2e);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) Z += sv[u].y * fast_exp2((sv[u].x - mx) * kLog2e);
+            M = mx;
+          }
+          xstat[q * 128 + r] = make_float2(M, Z);
+          epi_sync();
+          if (et < 128) {
+            float mx = -1e30f, z = 0.f;
+#pragma unroll
+            for (int g = 0; g < kParts; ++g) mx = fmaxf(mx, xstat[g * 128 + et].x);
+#pragma unroll
+            for (int g = 0; g < kParts; ++g) {
+              const float2 a = xstat[g * 128 + et];
+              z += a.y * fast_exp2((a.x - mx) * kLog2e);
+            }
+            crow[v * 128 + et] = ((VSEL(ublk, v) * 128 + et) / W < p.groups) ? (-mx * kLog2e - log2f(z)) : -INFINITY;
+          }
+          epi_sync();
+          DYN_STAMP(et == 0, 4 + v);
+        }
+        const int key = tile * kTile + r_loc;
+        const int head0 = (VSEL(ublk, v) * 128 + wg * 32) / W;
+        if (head0 >= p.groups) {  // this warpgroup's 32 columns are beyond the last head
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty(buf));
+        } else {
+          uint32_t vals[32];
+          tmem_ld32(tcol + buf * 128, vals);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty(buf));
           float2 acc[kHeadsPerChunk];
 #pragma unroll
           for (int h = 0; h < kHeadsPerChunk; ++h) acc[h] = make_float2(0.f, 0.f);
-          if (have) {
-            tmem_ld_wait();
-            tmem_ld16(tcol + (ts % kNumBuf) * 128 + 16, vb);
-            DYN_TSTAMP(et == 0, ts, 4);
-            p2_half<T, W, POLY2>(va, scale, cr, 0, acc);
-            tmem_ld_wait();
-            tc_fence_before();
-          }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(tempty(ts % kNumBuf));
-          KVC_NEXT_TILE(seg)
-          if (have) {
-            p2_half<T, W, POLY2>(vb, scale, cr + 16, 16, acc);
-            if (tile * kTile + r_loc < nscore) {
+          p2_chunk<T, W, POLY2>(vals, scale, crow + v * 128 + wg * 32, acc);
+          if (key < nscore) {
 #pragma unroll
-              for (int h = 0; h < kHeadsPerChunk; ++h)
-                if (head0 + h < p.groups)
-                  out0[(int64_t)h * nscore + tile * kTile] = T::round1((acc[h].x + acc[h].y) * inv_w);
+            for (int h = 0; h < kHeadsPerChunk; ++h) {
+              const int head = head0 + h;
+              if (head < p.groups) {
+                float sum = acc[h].x + acc[h].y;
+                if (p.reduce_mean) sum = sum / (float)p.w;
+                p.out[((int64_t)VSEL(ub, v) * p.Hq + VSEL(ukvh, v) * p.groups + head) * nscore + key] = T::round1(sum);
+              }
             }
           }
-          ++n2_tiles;
-          DYN_TSTAMP(et == 0, ts, 5);
-          KVC_NEXT_TILE_LATE()
-        } while (code >= 0 && (code & kSegMask) == seg);
+        }
+        ++n2_tiles;
       }
     }
-#undef KVC_NEXT_TILE
-#undef KVC_NEXT_TILE_LATE
     DYN_STAMP(et == 0, 6);
     DYN_STAMP(et == 0, 7, (long long)(n1_tiles * 1000 + n2_tiles));
-  } else {
-    // ===== stats warps: 64 threads, thread s owns query rows s and s + 64 of whatever unit is at hand =====
-    // (a) publish: combine the four column slices of a finished chunk (fixed order) and write the partial;
-    // (b) fold: once done[unit] says every chunk of a unit is published, fold the partials in chunk order into
-    //     c_row = -M log2e - log2 Z and hand it to the epilogue.  Both run beside the epilogue, which never stops for
-    //     them: x is folded while the epilogue is in y.pass1, y while it is in x.pass2.
-    const int st = tid - 32 * (2 + kEpiWarps);
-    int k = 0;
-    bool folded_0 = false, folded_1 = nvis < 2;
-    auto combine4 = [&](const float2* x4, int row) -> float2 {   // slices g = 0..3 of one row, 128 apart
-      float mn = -1e30f, z = 0.f;
-#pragma unroll
-      for (int g = 0; g < kNumWG; ++g) mn = fmaxf(mn, x4[g * 128 + row].x);
-#pragma unroll
-      for (int g = 0; g < kNumWG; ++g) {
-        const float2 a = x4[g * 128 + row];
-        z += a.y * fast_exp2((a.x - mn) * kLog2e);
-      }
-      return make_float2(mn, z);
-    };
-    for (unsigned idle = 0; !(folded_0 && folded_1);) {
-      bool worked = false;
-      if (mbar_try(pub_full(k & 1), (k >> 1) & 1)) {
-        const int slot = k & 1;
-        const int u = pubreq[slot].x, chunk = pubreq[slot].y;
-        float2* dst = p.stats + ((int64_t)u * p.max_chunks + chunk) * 128;
-        dst[st] = combine4(xstat + slot * kNumWG * 128, st);
-        dst[st + 64] = combine4(xstat + slot * kNumWG * 128, st + 64);
-        __threadfence();
-        __syncwarp();
-        if (lane == 0) { atomicAdd(&ctl->done[u], 1u); mbar_arrive(pub_empty(slot)); }
-        ++k;
-        worked = true;
-      }
-#pragma unroll
-      for (int v = 0; v < 2; ++v) {
-        if (VSEL(folded, v)) continue;
-        unsigned d = 0;
-        if (lane == 0) d = ld_acquire_u32(&ctl->done[VSEL(unit, v)]);
-        d = __shfl_sync(0xffffffffu, d, 0);
-        if (d < (unsigned)(VSEL(n1c, v) * kStatWarps)) continue;
-        // every chunk of the unit is published (each stats warp of each publishing CTA counted once)
-        const int nparts = VSEL(n1c, v);
-        const float2* src = p.stats + (int64_t)VSEL(unit, v) * p.max_chunks * 128;
-        float M0 = -1e30f, Z0 = 0.f, M1 = -1e30f, Z1 = 0.f;
-        for (int c0 = 0; c0 < nparts; c0 += 8) {
-          float2 sa[8], sb[8];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            sa[u] = sb[u] = make_float2(-1e30f, 0.f);
-            if (c0 + u < nparts) {
-              const float2* a = src + (int64_t)(c0 + u) * 128 + st;
-              asm volatile("ld.global.cg.v2.f32 {%0, %1}, [%2];" : "=f"(sa[u].x), "=f"(sa[u].y) : "l"(a) : "memory");  // written by other SMs: bypass L1
-              asm volatile("ld.global.cg.v2.f32 {%0, %1}, [%2];" : "=f"(sb[u].x), "=f"(sb[u].y) : "l"(a + 64) : "memory");
-            }
-          }
-          float mx = M0, my = M1;
-#pragma unroll
-          for (int u = 0; u < 8; ++u) { mx = fmaxf(mx, sa[u].x); my = fmaxf(my, sb[u].x); }
-          Z0 *= fast_exp2((M0 - mx) * kLog2e);
-          Z1 *= fast_exp2((M1 - my) * kLog2e);
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            Z0 += sa[u].y * fast_exp2((sa[u].x - mx) * kLog2e);
-            Z1 += sb[u].y * fast_exp2((sb[u].x - my) * kLog2e);
-          }
-          M0 = mx; M1 = my;
-        }
-        crow[v * 128 + st] = ((VSEL(ublk, v) * 128 + st) / W < p.groups) ? (-M0 * kLog2e - log2f(Z0)) : -INFINITY;
-        crow[v * 128 + st + 64] = ((VSEL(ublk, v) * 128 + st + 64) / W < p.groups) ? (-M1 * kLog2e - log2f(Z1)) : -INFINITY;
-        __syncwarp();
-        if (lane == 0) mbar_arrive(crow_ready(v));
-        if (v) folded_1 = true; else folded_0 = true;
-        worked = true;
-      }
-      if (worked) { idle = 0; continue; }
-      __nanosleep(200);
-      if (++idle > (1u << 23)) {
-        printf("kvc scores_dyn: statistics of units %d/%d never completed (block %d)\n", unit_0, unit_1, blockIdx.x);
-        __trap();
-      }
-    }
   }
 
   tc_fence_before();
@@ -656,9 +556,6 @@ static int dispatch_w(const CUtensorMap& tmap, const Params& sp, const Plan& pl,
 extern "C" int kvc_debug_dyn_trace(long long* out, int n) {
   return (int)cudaMemcpyFromSymbol(out, dyn::g_dtrace, sizeof(long long) * (size_t)n);
 }
-extern "C" int kvc_debug_dyn_tile_trace(unsigned* out) {
-  return (int)cudaMemcpyFromSymbol(out, dyn::g_ttrace, sizeof(unsigned) * 2 * 64 * 8);
-}
 #endif
 
 bool window_scores_tc_supported(int B, int Hq, int Hkv, int L, int d, int w);
@@ -700,8 +597,6 @@ int window_scores_dyn(const void* q, int64_t q_sb, int64_t q_sh, int64_t q_sl, c
   sp.nblk = pl.nblk; sp.units = pl.units; sp.nx = pl.nx; sp.ny = pl.ny; sp.max_chunks = pl.max_chunks;
   sp.scale = 1.0f / sqrtf((float)d);
   sp.reduce_mean = reduce == KVC_REDUCE_MEAN;
-  static const int stagger = [] { const char* e = getenv("KVC_DYN_STAGGER"); return e ? atoi(e) : 270; }();
-  sp.stagger = stagger;
   sp.stats = (float2*)workspace;
   sp.out = (uint16_t*)out_scores;
   sp.tl = KVC_TL_SLOT(0);

@@ -30,6 +30,8 @@ print("pass-1 tiles per CTA: min %d max %d sum %d;  pass-2: min %d max %d sum %d
 for c in (0, 1, 8, 70, 147):
     print("cta", c, [(x - t0) if x > 1000 else x for x in t[c]])
 
+if not hasattr(raw, "kvc_debug_dyn_tile_trace"):
+    sys.exit(0)          # the per-tile stamps exist only in experimental builds of scores_dyn.cu
 tb = (ctypes.c_uint * (2 * 64 * 8))()
 raw.kvc_debug_dyn_tile_trace(tb)
 for ci, cta in enumerate((0, 70)):
