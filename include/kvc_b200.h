@@ -41,8 +41,8 @@ enum { KVC_REDUCE_SUM = 0, KVC_REDUCE_MEAN = 1 };
 enum { KVC_IMPL_AUTO = 0, KVC_IMPL_MMA_SYNC = 1, KVC_IMPL_TCGEN05 = 2 /* two launches */,
        KVC_IMPL_TCGEN05_FUSED = 3 /* one cooperative launch with a grid barrier between the passes */,
        KVC_IMPL_TCGEN05_HALF = 4  /* same, half-footprint CTAs: two launches (two streams) share every SM */,
-       KVC_IMPL_TCGEN05_DYN = 5   /* one launch, tiles claimed dynamically per (batch, KV head) unit: no grid barrier,
-                                     no co-residency requirement (the default where the shape allows it) */ };
+       KVC_IMPL_TCGEN05_DYN = 5   /* one launch, work claimed dynamically per (batch, KV head, row block) unit: no grid
+                                     barrier and no co-residency requirement; AUTO uses it for more units than SMs */ };
 
 enum {
   KVC_OK = 0,

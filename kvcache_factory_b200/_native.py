@@ -242,6 +242,9 @@ def gather_dense(key_states: torch.Tensor, value_states: torch.Tensor, idx, num_
     e = key_states.element_size()
     k = _rowmajor_last(key_states, 16 // e)
     v = _rowmajor_last(value_states, 16 // e)
+    if v is not value_states and value_states.device.type == "cpu":
+        # a repacked copy would be pageable memory whose host address the kernel cannot read
+        raise RuntimeError("a pinned host value_states tensor must have a unit-stride last dim and 16-byte aligned rows")
     if idx is not None:
         _require_cuda(key_states, idx)
         if idx.dtype != torch.int32 or not idx.is_contiguous():

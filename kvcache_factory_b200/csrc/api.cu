@@ -166,15 +166,17 @@ int kvc_window_scores(const void* q, int64_t q_sb, int64_t q_sh, int64_t q_sl, c
   if (impl == KVC_IMPL_TCGEN05_DYN && !dyn_ok)
     return fail(KVC_ERR_UNSUPPORTED, "tcgen05 scoring kernel does not cover this shape (Hq/Hkv=%d, w=%d, d=%d, units=%d)",
                 Hq / Hkv, w, d, B * Hkv);
-  if (impl == KVC_IMPL_TCGEN05_DYN || (impl == KVC_IMPL_AUTO && dyn_ok && aligned))
-    return window_scores_dyn(q, q_sb, q_sh, q_sl, k, k_sb, k_sh, k_sl, B, Hq, Hkv, L, d, w, dtype, reduce, out_scores,
-                             workspace, workspace_bytes, (cudaStream_t)stream);
   if ((impl == KVC_IMPL_TCGEN05 && !tc_ok) || ((impl == KVC_IMPL_TCGEN05_FUSED || impl == KVC_IMPL_TCGEN05_HALF) && !fused_ok))
     return fail(KVC_ERR_UNSUPPORTED, "tcgen05 scoring kernel does not cover this shape (Hq/Hkv=%d, w=%d, d=%d)",
                 Hq / Hkv, w, d);
+  // IMPL_AUTO: the chunked single-launch kernel where its grid fits the SMs (fastest alone: 35 vs 38 us per cfg-2
+  // layer), the dynamically scheduled kernel for more units than SMs, then the two-launch tcgen05 kernel, then mma.sync
   if (impl == KVC_IMPL_TCGEN05_FUSED || impl == KVC_IMPL_TCGEN05_HALF || (impl == KVC_IMPL_AUTO && fused_ok && aligned))
     return window_scores_fused(q, q_sb, q_sh, q_sl, k, k_sb, k_sh, k_sl, B, Hq, Hkv, L, d, w, dtype, reduce, out_scores,
                                workspace, workspace_bytes, impl == KVC_IMPL_TCGEN05_HALF, (cudaStream_t)stream);
+  if (impl == KVC_IMPL_TCGEN05_DYN || (impl == KVC_IMPL_AUTO && dyn_ok && aligned))
+    return window_scores_dyn(q, q_sb, q_sh, q_sl, k, k_sb, k_sh, k_sl, B, Hq, Hkv, L, d, w, dtype, reduce, out_scores,
+                             workspace, workspace_bytes, (cudaStream_t)stream);
   if (impl == KVC_IMPL_TCGEN05 || (impl == KVC_IMPL_AUTO && tc_ok && aligned))
     return window_scores_tc(q, q_sb, q_sh, q_sl, k, k_sb, k_sh, k_sl, B, Hq, Hkv, L, d, w, dtype, reduce, out_scores,
                             workspace, workspace_bytes, (cudaStream_t)stream);

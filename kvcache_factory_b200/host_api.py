@@ -47,6 +47,7 @@ class HostCompressor:
             self._out = [None] * n
         ev_in = [torch.cuda.Event() for _ in range(n)]
         ev_done = [torch.cuda.Event() for _ in range(n)]
+        ev_out = [torch.cuda.Event() for _ in range(n)]
         keep = []
         h2d = d2h = 0
         self.s_in.wait_stream(cur)
@@ -54,7 +55,9 @@ class HostCompressor:
             dk, dv, dq = stage[l % 2]
             with torch.cuda.stream(self.s_in):
                 if l >= 2:
-                    self.s_in.wait_event(ev_done[l - 2])           # staging set is free again
+                    self.s_in.wait_event(ev_done[l - 2])           # staging set is free again ...
+                    self.s_in.wait_event(ev_out[l - 2])            # ... also for the output copies: on the pass-through
+                                                                   # branch K' IS the staging buffer
                 dk.copy_(host_k[l], non_blocking=True)
                 if not self.zero_copy_v:
                     dv.copy_(host_v[l], non_blocking=True)
@@ -83,6 +86,7 @@ class HostCompressor:
                 self.s_out.wait_event(ev_done[l])
                 self._out[l][0].copy_(kc, non_blocking=True)
                 self._out[l][1].copy_(vc, non_blocking=True)
+                ev_out[l].record(self.s_out)
             keep.append((kc, vc))
             d2h += 2 * kc.numel() * kc.element_size()
         self.s_out.synchronize()

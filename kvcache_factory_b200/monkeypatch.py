@@ -71,12 +71,44 @@ class _GroupsView:
 
 def _layer_keys(past_key_values, layer_idx: int) -> Optional[torch.Tensor]:
     layers = getattr(past_key_values, "layers", None)
-    if layers is None or layer_idx >= len(layers):
+    if layers is None:
+        # Without the per-layer view there is no way to tell prefill from decode: every decode step would be
+        # compressed as a one-token "prefill" and attention would silently see only the current token.
+        raise TypeError(f"kvcache_factory_b200 hooks need a transformers >= 4.54 layered cache (DynamicCache with "
+                        f".layers); got {type(past_key_values).__name__}")
+    if layer_idx >= len(layers):
         return None
     keys = getattr(layers[layer_idx], "keys", None)
     if keys is None or not getattr(layers[layer_idx], "is_initialized", True) or keys.numel() == 0:
         return None
     return keys
+
+
+def _store_prefill(past_key_values, kc: torch.Tensor, vc: torch.Tensor, layer_idx: int, pending: bool) -> None:
+    """Hand the compressed rows to the HF cache (``llama_model.py:399-404``).  ``DynamicLayer.update`` concatenates
+    onto an empty tensor, i.e. READS the rows on the caller's stream; with ``async_tail`` they are still being
+    gathered on a side stream, so the layer is created with empty slices (no data is touched) and the tensors are
+    attached as they are -- which also saves a copy of the compressed cache in the synchronous case.  The first decode
+    step joins the side streams (``_join_compression``)."""
+    if kc.dim() == 4 and hasattr(past_key_values, "layers"):
+        past_key_values.update(kc[:, :, :0], vc[:, :, :0], layer_idx)
+        layer = past_key_values.layers[layer_idx]
+        # plain DynamicLayer only: sliding-window / quantised layers keep their own bookkeeping in update()
+        if type(layer).__name__ == "DynamicLayer" and layer.keys.shape[-2] == 0:
+            layer.keys, layer.values = kc, vc
+            if pending:
+                past_key_values.__dict__["_kvc_pending"] = True
+            return
+    if pending:
+        U.wait_for_compression(kc.device)
+    past_key_values.update(kc, vc, layer_idx)
+
+
+def _join_compression(past_key_values, device) -> None:
+    """Before the compressed cache is read for the first time: wait for the asynchronous select/gather tails."""
+    if past_key_values.__dict__.get("_kvc_pending"):
+        U.wait_for_compression(device)
+        past_key_values.__dict__["_kvc_pending"] = False
 
 
 def _make_forward(method: str, family):
@@ -110,8 +142,9 @@ def _make_forward(method: str, family):
             k_att, v_att = key_states, value_states                   # attention sees the whole prompt
             kc, vc = self.kv_cluster.update_kv(key_states, query_states, value_states, attention_mask,
                                                self.num_key_value_groups)
-            past_key_values.update(kc, vc, self.layer_idx)
+            _store_prefill(past_key_values, kc, vc, self.layer_idx, getattr(self.kv_cluster, "async_tail", False))
         else:                                                         # ---- decode ----
+            _join_compression(past_key_values, hidden_states.device)
             self.kv_seq_len = getattr(self, "kv_seq_len", 0) + q_len
             cached = _layer_keys(past_key_values, self.layer_idx)
             if cached.shape[1] != key_states.shape[1]:                # compressed cache: one K/V head per query head

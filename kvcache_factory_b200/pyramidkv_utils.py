@@ -38,7 +38,13 @@ _tail_turn = {}
 NUM_TAIL_STREAMS = int(os.environ.get("KVC_TAIL_STREAMS", "3"))
 # gathers on their own rotating streams (a stream's next select then never waits behind a gather): 1.66 -> 1.60 ms
 NUM_GATHER_STREAMS = int(os.environ.get("KVC_GATHER_STREAMS", "2"))
-NUM_SCORE_STREAMS = int(os.environ.get("KVC_SCORE_STREAMS", "4"))   # async_scores: two half-footprint launches share an SM; 2 -> 1.45, 4 -> 1.43 ms
+# async_scores: the half-footprint scoring kernel synchronises its CTAs with a grid barrier, so every launch in flight
+# must be fully resident.  Two launches of <= #SMs CTAs always are (two such CTAs fit one SM: ~100 KB of shared
+# memory, 256 of 512 TMEM columns, 2 x 320 threads x 96 registers each), so at most TWO are ever in flight: launch n
+# goes to stream n % 2 and launches of one stream serialise.  More streams (4 measured 1.43 vs 1.46 ms per cfg-2 step)
+# would leave three partially resident barrier grids waiting for each other's SMs with nothing but the block
+# scheduler's FIFO order against a deadlock, so the value is capped.
+NUM_SCORE_STREAMS = max(1, min(2, int(os.environ.get("KVC_SCORE_STREAMS", "2"))))
 
 
 def compression_stream(device, which: int = None) -> "torch.cuda.Stream":
@@ -59,11 +65,32 @@ def compression_stream(device, which: int = None) -> "torch.cuda.Stream":
 
 
 def wait_for_compression(device=None) -> None:
-    """Make the current stream wait for every asynchronous select/gather issued so far."""
-    want = None if device is None else (torch.device(device).index or 0)
+    """Make the current stream wait for every asynchronous scoring / select / gather issued so far."""
+    want = None
+    if device is not None:
+        device = torch.device(device)
+        want = device.index if device.index is not None else torch.cuda.current_device()
     for (dev_index, _), stream in list(_side_streams.items()):
         if want is None or dev_index == want:
             torch.cuda.current_stream(dev_index).wait_stream(stream)
+
+
+def _flag(config, name: str, env: str) -> bool:
+    """Opt-in switch: attribute on the (HF) config the reference's drivers write their knobs to, else an
+    environment variable; off by default, like every behaviour the reference does not have."""
+    if config is not None and hasattr(config, name):
+        return bool(getattr(config, name))
+    return os.environ.get(env, "0") == "1"
+
+
+def _apply_async_knobs(cluster, config) -> None:
+    """``config.kvc_async_tail`` / ``config.kvc_async_scores`` (or KVC_ASYNC_TAIL=1 / KVC_ASYNC_SCORES=1): the
+    clusters are rebuilt on every forward (reference ``:894,918,1003,1025``), so the switches live on the config the
+    ``init_*`` helpers read, not on a cluster instance.  A caller that turns them on must call
+    ``wait_for_compression()`` before it reads the compressed cache (``monkeypatch.py`` does, at the first decode
+    step)."""
+    cluster.async_tail = _flag(config, "kvc_async_tail", "KVC_ASYNC_TAIL")
+    cluster.async_scores = cluster.async_tail and _flag(config, "kvc_async_scores", "KVC_ASYNC_SCORES")
 
 
 def _trace(msg: str) -> None:
@@ -560,6 +587,7 @@ def init_pyramidkv(self, num_hidden_layers):
         num_hidden_layers=num_hidden_layers, layer_idx=self.layer_idx, window_size=self.config.window_size,
         max_capacity_prompt=self.config.max_capacity_prompt, kernel_size=self.config.kernel_size,
         pooling=self.config.pooling, merge=self.config.merge)
+    _apply_async_knobs(self.kv_cluster, self.config)
 
 
 def init_snapkv(self):
@@ -569,6 +597,7 @@ def init_snapkv(self):
     self.kv_cluster = SnapKVCluster(
         window_size=self.config.window_size, max_capacity_prompt=self.config.max_capacity_prompt,
         kernel_size=self.config.kernel_size, pooling=self.config.pooling, merge=self.config.merge)
+    _apply_async_knobs(self.kv_cluster, self.config)
 
 
 def init_H2O(self):
@@ -578,6 +607,7 @@ def init_H2O(self):
     self.kv_cluster = H2OKVCluster(
         window_size=self.config.window_size, max_capacity_prompt=self.config.max_capacity_prompt,
         kernel_size=self.config.kernel_size, pooling=self.config.pooling, merge=self.config.merge)
+    _apply_async_knobs(self.kv_cluster, self.config)
 
 
 def init_StreamingLLM(self):
@@ -587,6 +617,7 @@ def init_StreamingLLM(self):
     self.kv_cluster = StreamingLLMKVCluster(
         window_size=self.config.window_size, max_capacity_prompt=self.config.max_capacity_prompt,
         kernel_size=self.config.kernel_size, pooling=self.config.pooling, merge=self.config.merge)
+    _apply_async_knobs(self.kv_cluster, self.config)
 
 
 def init_adakv(self):
