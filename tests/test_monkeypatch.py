@@ -178,3 +178,42 @@ def test_adakv_hook_flattened_cache_and_varlen_decode():
         assert int(lens.min()) >= int((cap - w) * 0.2) + w + new - 1
         assert torch.equal(cl.cu_klen.cpu()[1:] - cl.cu_klen.cpu()[:-1], lens)
         assert cl.max_seqlen_k >= int(lens.max())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("method", ["snapkv", "pyramidkv"])
+def test_async_knobs_through_the_hooks_equal_the_synchronous_path(method, monkeypatch):
+    """config.kvc_async_tail / kvc_async_scores are read by init_* on every forward (the clusters are rebuilt each
+    time), the hook attaches the still-being-gathered rows to the HF cache without reading them and joins the side
+    streams before the first decode read: same tokens, same cache, bit for bit."""
+    dev = torch.device("cuda:0")
+    # the asynchronous scoring path runs the half-footprint kernel; pin it for the synchronous runs too so that the
+    # three runs are bit-comparable (the kernels differ in the grouping of the fp32 partial sums)
+    monkeypatch.setattr(U._ScoredCluster, "score_impl", kvc._native.IMPL_TCGEN05_HALF)
+    model = tiny(dtype=torch.bfloat16, head_dim=128, layers=4).to(dev)
+    kvc.replace_llama(method)
+    model.config.max_capacity_prompt, model.config.window_size, model.config.kernel_size = 256, 32, 7
+    model.config.pooling = "avgpool"
+    ids = torch.randint(0, 97, (1, 3000), generator=torch.Generator().manual_seed(5)).to(dev)
+    runs = []
+    for flags in ((False, False), (True, False), (True, True)):
+        model.config.kvc_async_tail, model.config.kvc_async_scores = flags
+        out = model.generate(ids, max_new_tokens=6, do_sample=False, use_cache=True, return_dict_in_generate=True)
+        torch.cuda.synchronize()
+        assert isinstance(model.model.layers[0].self_attn.kv_cluster.async_tail, bool)
+        assert model.model.layers[0].self_attn.kv_cluster.async_tail == flags[0]
+        runs.append((out.sequences.cpu(), [l.keys.cpu() for l in out.past_key_values.layers],
+                     [l.values.cpu() for l in out.past_key_values.layers]))
+    for seq, ks, vs in runs[1:]:
+        assert torch.equal(seq, runs[0][0])
+        for a, b in zip(ks, runs[0][1]):
+            assert torch.equal(a, b)
+        for a, b in zip(vs, runs[0][2]):
+            assert torch.equal(a, b)
+
+
+def test_hooks_refuse_a_cache_without_layers():
+    class OldCache:                      # transformers < 4.54 style: no per-layer view
+        key_cache, value_cache = [], []
+    with pytest.raises(TypeError, match="layered cache"):
+        MP._layer_keys(OldCache(), 0)
