@@ -72,7 +72,15 @@ def wait_for_compression(device=None) -> None:
         want = device.index if device.index is not None else torch.cuda.current_device()
     for (dev_index, _), stream in list(_side_streams.items()):
         if want is None or dev_index == want:
-            torch.cuda.current_stream(dev_index).wait_stream(stream)
+            cur = torch.cuda.current_stream(dev_index)
+            if _capturing(cur) and not _capturing(stream):
+                continue      # CUDA-graph capture: a side stream that was never forked into this capture holds none of its work
+            cur.wait_stream(stream)
+
+
+def _capturing(stream) -> bool:
+    with torch.cuda.stream(stream):
+        return torch.cuda.is_current_stream_capturing()
 
 
 def _flag(config, name: str, env: str) -> bool:
