@@ -183,6 +183,23 @@ int kvc_update_flatten_view(void* dst, const void* src, const void* state,
                             const int32_t* headlens, const int32_t* cu_headlens,
                             int H, int d, int elem_bytes, int64_t total_rows, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Slack layout of the flattened cache: O(H*d) decode append.  No reference
+ * counterpart: the reference rebuilds the whole layer cache on every decoded token
+ * (pyramidkv/pyramidkv_utils.py:52-75 -> cuda_api.cu:55-85); these two entry points replace that with
+ * an in-place write of H rows plus a re-layout every `slack` tokens.
+ *
+ * Buffers are [cu_cap[H], d]; head h owns rows [cu_cap[h], cu_cap[h+1]) and uses the first
+ * head_lens[h].  kvc_append_rows writes new_k[h] / new_v[h] ([H, d]) to row cu_cap[h]+head_lens[h]
+ * of k_buf / v_buf (heads without slack left are skipped; head_lens is NOT modified: the caller bumps
+ * it, as llama_model.py:2375 does).  kvc_flatten_regrow moves head h's head_lens[h] rows from src rows
+ * [cu_src[h], ...) to dst rows [cu_dst[h], ...) (src/dst must not overlap).
+ * ---------------------------------------------------------------------------------------------- */
+int kvc_append_rows(void* k_buf, void* v_buf, const void* new_k, const void* new_v, const int32_t* cu_cap,
+                    const int32_t* head_lens, int H, int d, int elem_bytes, void* stream);
+int kvc_flatten_regrow(void* dst, const void* src, const int32_t* head_lens, const int32_t* cu_src,
+                       const int32_t* cu_dst, int H, int d, int elem_bytes, int64_t total_rows, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

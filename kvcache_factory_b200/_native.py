@@ -48,6 +48,8 @@ _SIGNATURES = {
     "kvc_adakv_allocate": (c_int, [_p, _p, _i, _i, _i, _i, c_float, _i, _i, _i, _p, _p, _p, _p, c_size_t, _p]),
     "kvc_adakv_key_histogram": (c_int, [_p, _p, _i, _i, _i, _i, _p, _p]),
     "kvc_update_flatten_view": (c_int, [_p, _p, _p, _p, _p, _i, _i, _i, _i64, _p]),
+    "kvc_append_rows": (c_int, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p]),
+    "kvc_flatten_regrow": (c_int, [_p, _p, _p, _p, _p, _i, _i, _i, _i64, _p]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
@@ -333,6 +335,36 @@ def update_flatten_view(cache: torch.Tensor, state: torch.Tensor, headlens: torc
             out.data_ptr(), cache.data_ptr(), state.data_ptr(), headlens.data_ptr(), cu_headlens.data_ptr(),
             H, d, cache.element_size(), total, _stream(dev)))
     return out
+
+
+def append_rows(k_buf: torch.Tensor, v_buf: torch.Tensor, new_k: torch.Tensor, new_v: torch.Tensor,
+                cu_cap: torch.Tensor, head_lens: torch.Tensor) -> None:
+    """In place: new_k[h] / new_v[h] -> row cu_cap[h] + head_lens[h] of the slack-layout buffers (O(H*d))."""
+    dev = _require_cuda(k_buf, v_buf, new_k, new_v, cu_cap, head_lens)
+    if cu_cap.dtype != torch.int32 or head_lens.dtype != torch.int32:
+        raise RuntimeError("expected cu_cap / head_lens to be int32")
+    dtype_code(k_buf.dtype)
+    H, d = new_k.shape
+    if not (k_buf.is_contiguous() and v_buf.is_contiguous()):
+        raise RuntimeError("slack-layout cache buffers must be contiguous")
+    with torch.cuda.device(dev):
+        _check("kvc_append_rows", lib().kvc_append_rows(
+            k_buf.data_ptr(), v_buf.data_ptr(), new_k.contiguous().data_ptr(), new_v.contiguous().data_ptr(),
+            cu_cap.data_ptr(), head_lens.data_ptr(), H, d, k_buf.element_size(), _stream(dev)))
+
+
+def flatten_regrow(src: torch.Tensor, head_lens: torch.Tensor, cu_src: torch.Tensor, cu_dst: torch.Tensor,
+                   total_dst_rows: int) -> torch.Tensor:
+    """New [total_dst_rows, d] buffer with head h's head_lens[h] rows moved from src row cu_src[h] to row cu_dst[h]."""
+    dev = _require_cuda(src, head_lens, cu_src, cu_dst)
+    dtype_code(src.dtype)
+    H, d = head_lens.shape[0], src.shape[1]
+    dst = torch.empty((total_dst_rows, d), dtype=src.dtype, device=dev)
+    with torch.cuda.device(dev):
+        _check("kvc_flatten_regrow", lib().kvc_flatten_regrow(
+            dst.data_ptr(), src.contiguous().data_ptr(), head_lens.data_ptr(), cu_src.data_ptr(), cu_dst.data_ptr(),
+            H, d, src.element_size(), src.shape[0], _stream(dev)))
+    return dst
 
 
 def launch_count() -> int:

@@ -13,6 +13,8 @@ int gather_dense(const void*, int64_t, int64_t, int64_t, const void*, int64_t, i
                  int, int, int, int, int, int, int, void*, void*, cudaStream_t);
 int gather_varlen(const void*, int64_t, int64_t, const void*, int64_t, int64_t, const int32_t*, int64_t,
                   const int32_t*, const int32_t*, int, int, int, int, int, int, int, void*, void*, cudaStream_t);
+int append_rows(void*, void*, const void*, const void*, const int32_t*, const int32_t*, int, int, int, cudaStream_t);
+int flatten_regrow(void*, const void*, const int32_t*, const int32_t*, const int32_t*, int, int, int, int64_t, cudaStream_t);
 int update_flatten_view(void*, const void*, const void*, const int32_t*, const int32_t*, int, int, int, int64_t,
                         cudaStream_t);
 size_t pool_topk_workspace_bytes(int rows, int n, int k);
@@ -284,6 +286,24 @@ int kvc_update_flatten_view(void* dst, const void* src, const void* state, const
               "elem_bytes %d: the reference kernel is fp16/bf16 only (static_switch.h:3-12)", elem_bytes);
   return update_flatten_view(dst, src, state, headlens, cu_headlens, H, d, elem_bytes, total_rows,
                              (cudaStream_t)stream);
+}
+
+int kvc_append_rows(void* k_buf, void* v_buf, const void* new_k, const void* new_v, const int32_t* cu_cap,
+                    const int32_t* head_lens, int H, int d, int elem_bytes, void* stream) {
+  if (int rc = check_device()) return rc;
+  KVC_REQUIRE(k_buf && v_buf && new_k && new_v && cu_cap && head_lens, KVC_ERR_ARG, "null pointer argument");
+  KVC_REQUIRE(H > 0 && d > 0, KVC_ERR_ARG, "H=%d d=%d", H, d);
+  KVC_REQUIRE(elem_bytes == 2, KVC_ERR_UNSUPPORTED, "elem_bytes %d: the flattened cache is fp16/bf16", elem_bytes);
+  return append_rows(k_buf, v_buf, new_k, new_v, cu_cap, head_lens, H, d, elem_bytes, (cudaStream_t)stream);
+}
+
+int kvc_flatten_regrow(void* dst, const void* src, const int32_t* head_lens, const int32_t* cu_src,
+                       const int32_t* cu_dst, int H, int d, int elem_bytes, int64_t total_rows, void* stream) {
+  if (int rc = check_device()) return rc;
+  KVC_REQUIRE(dst && src && head_lens && cu_src && cu_dst, KVC_ERR_ARG, "null pointer argument");
+  KVC_REQUIRE(H > 0 && d > 0 && total_rows >= 0, KVC_ERR_ARG, "H=%d d=%d total_rows=%lld", H, d, (long long)total_rows);
+  KVC_REQUIRE(elem_bytes == 2, KVC_ERR_UNSUPPORTED, "elem_bytes %d: the flattened cache is fp16/bf16", elem_bytes);
+  return flatten_regrow(dst, src, head_lens, cu_src, cu_dst, H, d, elem_bytes, total_rows, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -165,4 +165,66 @@ int update_flatten_view(void* dst, const void* src, const void* state, const int
   return launch_status("flatten_append_kernel");
 }
 
+// ---- slack layout of the flattened cache: O(H*d) decode append ----------------------
+// Head h owns rows [cu_cap[h], cu_cap[h+1]) of the buffer and uses the first head_lens[h] of them.
+// append: the new row of head h goes to row cu_cap[h] + head_lens[h] of the K and of the V buffer (the caller bumps
+// head_lens afterwards, as the reference's forward does, llama_model.py:2372-2375).  One CTA per head and tensor.
+__global__ void __launch_bounds__(32)
+append_rows_kernel(char* __restrict__ kbuf, char* __restrict__ vbuf, const char* __restrict__ knew,
+                   const char* __restrict__ vnew, const int32_t* __restrict__ cu_cap,
+                   const int32_t* __restrict__ head_lens, int rowbytes) {
+  const int h = blockIdx.x;
+  const int len = head_lens[h];
+  if (len >= cu_cap[h + 1] - cu_cap[h]) return;   // no slack left: the host regrows before this can happen
+  char* dst = (blockIdx.y ? vbuf : kbuf) + ((int64_t)cu_cap[h] + len) * rowbytes;
+  const char* src = (blockIdx.y ? vnew : knew) + (int64_t)h * rowbytes;
+  if (threadIdx.x < rowbytes / 16) st_stream16(dst + threadIdx.x * 16, ld_stream16(src + threadIdx.x * 16));
+}
+
+// regrow / re-layout: head h's head_lens[h] rows move from src rows [cu_src[h], ...) to dst rows [cu_dst[h], ...).
+__global__ void __launch_bounds__(kFlatThreads)
+flatten_regrow_kernel(char* __restrict__ dst, const char* __restrict__ src, const int32_t* __restrict__ head_lens,
+                      const int32_t* __restrict__ cu_src, const int32_t* __restrict__ cu_dst, int rowbytes) {
+  const int h = blockIdx.y;
+  const int64_t nchunks = (int64_t)head_lens[h] * rowbytes / 16;
+  const char* s = src + (int64_t)cu_src[h] * rowbytes;
+  char* d = dst + (int64_t)cu_dst[h] * rowbytes;
+  const int64_t stride = (int64_t)gridDim.x * kFlatThreads;
+  int64_t i = (int64_t)blockIdx.x * kFlatThreads + threadIdx.x;
+  for (; i + (kFlatUnroll - 1) * stride < nchunks; i += kFlatUnroll * stride) {
+    int4 t[kFlatUnroll];
+#pragma unroll
+    for (int u = 0; u < kFlatUnroll; ++u) t[u] = ld_stream16(s + (i + u * stride) * 16);
+#pragma unroll
+    for (int u = 0; u < kFlatUnroll; ++u) st_stream16(d + (i + u * stride) * 16, t[u]);
+  }
+  for (; i < nchunks; i += stride) st_stream16(d + i * 16, ld_stream16(s + i * 16));
+}
+
+int append_rows(void* kbuf, void* vbuf, const void* knew, const void* vnew, const int32_t* cu_cap,
+                const int32_t* head_lens, int H, int d, int e, cudaStream_t stream) {
+  const int rowbytes = d * e;
+  KVC_REQUIRE(rowbytes % 16 == 0 && rowbytes <= 512, KVC_ERR_UNSUPPORTED, "row of %d bytes: need a multiple of 16, <= 512", rowbytes);
+  KVC_REQUIRE(aligned16(kbuf) && aligned16(vbuf) && aligned16(knew) && aligned16(vnew), KVC_ERR_UNSUPPORTED,
+              "cache/state pointers must be 16-byte aligned");
+  append_rows_kernel<<<dim3(H, 2), 32, 0, stream>>>((char*)kbuf, (char*)vbuf, (const char*)knew, (const char*)vnew, cu_cap,
+                                                   head_lens, rowbytes);
+  return launch_status("append_rows_kernel");
+}
+
+int flatten_regrow(void* dst, const void* src, const int32_t* head_lens, const int32_t* cu_src, const int32_t* cu_dst,
+                   int H, int d, int e, int64_t total_rows, cudaStream_t stream) {
+  const int rowbytes = d * e;
+  KVC_REQUIRE(rowbytes % 16 == 0, KVC_ERR_UNSUPPORTED, "row of %d bytes is not a multiple of 16", rowbytes);
+  KVC_REQUIRE(aligned16(dst) && aligned16(src), KVC_ERR_UNSUPPORTED, "cache pointers must be 16-byte aligned");
+  const int64_t chunks_per_head = (total_rows * rowbytes / 16 + H - 1) / H;
+  int64_t gx = (chunks_per_head + (int64_t)kFlatThreads * kFlatUnroll - 1) / ((int64_t)kFlatThreads * kFlatUnroll);
+  const int64_t cap_x = (int64_t)(8 * sm_count() + H - 1) / H;
+  if (gx > cap_x) gx = cap_x;
+  if (gx < 1) gx = 1;
+  flatten_regrow_kernel<<<dim3((unsigned)gx, H), kFlatThreads, 0, stream>>>((char*)dst, (const char*)src, head_lens, cu_src,
+                                                                           cu_dst, rowbytes);
+  return launch_status("flatten_regrow_kernel");
+}
+
 }  // namespace kvc

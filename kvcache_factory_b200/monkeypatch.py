@@ -27,6 +27,7 @@ AdaKV / HeadKV keep per-head lengths in the flattened ``[sum_h len_h, d]`` layou
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, Dict, Optional
 
 import torch
@@ -187,7 +188,9 @@ def _make_flat_forward(method: str, family):
         # cache object HF created for this generate() call.
         store = past_key_values
         if not isinstance(store, U.DynamicCacheSplitHeadFlatten):
-            store = past_key_values.__dict__.setdefault("_kvc_flat", U.DynamicCacheSplitHeadFlatten())
+            # config.kvc_decode_slack (or KVC_DECODE_SLACK): rows of slack per head segment -> O(H*d) decode appends
+            slack = int(getattr(self.config, "kvc_decode_slack", os.environ.get("KVC_DECODE_SLACK", "0")))
+            store = past_key_values.__dict__.setdefault("_kvc_flat", U.DynamicCacheSplitHeadFlatten(slack=slack))
         past_key_values = store
         if len(past_key_values) <= self.layer_idx:                    # ---- prefill ----
             _init_cluster(self, method)
@@ -196,7 +199,8 @@ def _make_flat_forward(method: str, family):
             attn_output, attn_weights = interface(self, query_states, key_states, value_states, attention_mask,
                                                   dropout=0.0, scaling=self.scaling, **kwargs)
             flat_k, flat_v = self.kv_cluster.update_kv(key_states, query_states, value_states)
-            past_key_values.update(flat_k, flat_v, self.layer_idx)
+            past_key_values.update(flat_k, flat_v, self.layer_idx,
+                                   {"head_lens": self.kv_cluster.head_lens, "cu_klen": self.kv_cluster.cu_klen})
             attn_output = attn_output.reshape(*input_shape, -1).contiguous()
         else:                                                         # ---- decode (llama_model.py:2362-2389) ----
             from flash_attn import flash_attn_varlen_func
@@ -210,11 +214,19 @@ def _make_flat_forward(method: str, family):
                                                     {"head_lens": c.head_lens, "cu_klen": c.cu_klen})
             c.klen_sum += num_heads
             c.max_seqlen_k += 1
-            c.cu_klen += c.cu_offset
             c.head_lens += 1
             q = query_states.reshape(-1, 1, self.head_dim)
-            attn_output = flash_attn_varlen_func(q, flat_k.view(-1, 1, self.head_dim), flat_v.view(-1, 1, self.head_dim),
-                                                 c.cu_qlen, c.cu_klen, 1, c.max_seqlen_k, causal=True)
+            cu_cap = past_key_values.cu_cap[self.layer_idx] if past_key_values.slack > 0 else None
+            if cu_cap is not None:
+                # slack layout: segment STARTS + USED lengths instead of packed cu_seqlens (the rows were written in place)
+                from flash_attn.flash_attn_interface import _flash_attn_varlen_forward
+                attn_output = _flash_attn_varlen_forward(
+                    q, flat_k.view(-1, 1, self.head_dim), flat_v.view(-1, 1, self.head_dim), c.cu_qlen, cu_cap, 1,
+                    c.max_seqlen_k, 0.0, self.head_dim ** -0.5, True, seqused_k=c.head_lens)[0]
+            else:
+                c.cu_klen += c.cu_offset
+                attn_output = flash_attn_varlen_func(q, flat_k.view(-1, 1, self.head_dim), flat_v.view(-1, 1, self.head_dim),
+                                                     c.cu_qlen, c.cu_klen, 1, c.max_seqlen_k, causal=True)
             attn_output = attn_output.reshape(bsz, num_heads, q_len, self.head_dim).transpose(1, 2)
             attn_output = attn_output.reshape(bsz, q_len, -1).contiguous()
             attn_weights = None

@@ -526,10 +526,32 @@ class DynamicCacheSplitHeadFlatten:
     same methods without inheriting (duck-typed use by the AdaKV forwards is unchanged).
     """
 
-    def __init__(self) -> None:
+    def __init__(self, slack: int = 0) -> None:
         self.key_cache: List[torch.Tensor] = []
         self.value_cache: List[torch.Tensor] = []
         self._seen_tokens = 0
+        # slack > 0 (not in the reference; SURVEY.md section 8 f3): every head's segment is allocated `slack` rows
+        # longer than it is, a decode step writes its H new rows in place (O(H*d) instead of recopying the whole layer
+        # cache, reference :57-72), and the layout is rebuilt with fresh slack every `slack` steps.  The attention then
+        # takes per-head START offsets (``cu_cap``) and USED lengths (``head_lens``) instead of packed cu_seqlens.
+        self.slack = int(slack)
+        self.cu_cap: List[Optional[torch.Tensor]] = []   # per layer: int32 [H+1] segment starts (slack layout only)
+        self._room: List[int] = []                        # per layer: appends left before the next re-layout
+
+    def _relayout(self, layer_idx: int, k: torch.Tensor, v: torch.Tensor, head_lens: torch.Tensor,
+                  cu_src: torch.Tensor) -> None:
+        H = head_lens.shape[0]
+        cu_dst = torch.zeros(H + 1, dtype=torch.int32, device=k.device)
+        cu_dst[1:] = (head_lens + self.slack).cumsum(0)
+        # total destination rows = used rows + H * slack; used rows = sum(head_lens) is known on the host: the packed
+        # prefill tensor has exactly that many rows, a slack buffer has H * slack more than its used rows had at
+        # the previous re-layout plus the H * slack appends since
+        used = self._used_rows[layer_idx]
+        total = used + H * self.slack
+        self.key_cache[layer_idx] = N.flatten_regrow(k, head_lens, cu_src, cu_dst, total)
+        self.value_cache[layer_idx] = N.flatten_regrow(v, head_lens, cu_src, cu_dst, total)
+        self.cu_cap[layer_idx] = cu_dst
+        self._room[layer_idx] = self.slack
 
     def __len__(self):
         return len(self.key_cache)
@@ -547,6 +569,25 @@ class DynamicCacheSplitHeadFlatten:
         if len(self.key_cache) <= layer_idx:
             self.key_cache.append(key_states)
             self.value_cache.append(value_states)
+            self.cu_cap.append(None)
+            self._room.append(0)
+            if not hasattr(self, "_used_rows"):
+                self._used_rows = []
+            self._used_rows.append(int(key_states.shape[0]) if key_states.dim() == 2 else 0)
+            if self.slack > 0 and key_states.dim() == 2 and cache_kwargs is not None:
+                # prefill hand-over of the packed [sum_h len_h, d] tensors: move them into the slack layout once
+                self._relayout(layer_idx, key_states, value_states, cache_kwargs["head_lens"], cache_kwargs["cu_klen"])
+        elif self.slack > 0 and self.cu_cap[layer_idx] is not None:
+            bs, head, seqlen, dim = key_states.shape
+            assert bs == 1 and seqlen == 1
+            head_lens = cache_kwargs["head_lens"]
+            if self._room[layer_idx] == 0:       # every head has used its slack (all heads grow by one row per step)
+                self._relayout(layer_idx, self.key_cache[layer_idx], self.value_cache[layer_idx], head_lens,
+                               self.cu_cap[layer_idx])
+            N.append_rows(self.key_cache[layer_idx], self.value_cache[layer_idx], key_states.view(-1, dim),
+                          value_states.view(-1, dim), self.cu_cap[layer_idx], head_lens)
+            self._room[layer_idx] -= 1
+            self._used_rows[layer_idx] += head
         else:
             assert self.key_cache[layer_idx].dim() == 2
             bs, head, seqlen, dim = key_states.shape

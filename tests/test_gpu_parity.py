@@ -198,6 +198,47 @@ def test_flatten_cache_decode_steps():
         assert torch.equal(k.cpu(), torch.cat(per_head, 0)) and torch.equal(v.cpu(), torch.cat(per_head, 0))
 
 
+@pytest.mark.parametrize("slack", [1, 5, 16])
+def test_slack_flatten_cache_equals_rebuild_path(slack):
+    """f3: in-place O(H*d) appends into slack-allocated head segments (re-laid out every `slack` steps) hold exactly
+    the rows the reference's rebuild-every-step cache holds, and flash-attn over (segment starts, used lengths) gives
+    the attention output of flash-attn over the packed cache, for 40 decode steps."""
+    from flash_attn import flash_attn_varlen_func
+    from flash_attn.flash_attn_interface import _flash_attn_varlen_forward
+    H, d = 8, 128
+    lens = [130, 7, 64, 999, 1, 33, 250, 512]
+    cache, _, hl, cu = _flatten_case(H, d, lens, torch.bfloat16, seed=3)
+    vcache = torch.randn(cache.shape, generator=torch.Generator().manual_seed(9)).to(torch.bfloat16)
+    ref, slk = DynamicCacheSplitHeadFlatten(), DynamicCacheSplitHeadFlatten(slack=slack)
+    hl_r, cu_r = torch.from_numpy(hl).to(dev()), torch.from_numpy(cu).to(dev())
+    hl_s = hl_r.clone()
+    ref.update(cache.to(dev()), vcache.to(dev()), 0)
+    slk.update(cache.to(dev()), vcache.to(dev()), 0, {"head_lens": hl_s, "cu_klen": cu_r.clone()})
+    off = torch.arange(0, H + 1, dtype=torch.int32, device=dev())
+    cu_q = torch.arange(0, H + 1, dtype=torch.int32, device=dev())
+    g = torch.Generator().manual_seed(21)
+    for step in range(40):
+        nk = torch.randn(1, H, 1, d, generator=g).to(torch.bfloat16).to(dev())
+        nv = torch.randn(1, H, 1, d, generator=g).to(torch.bfloat16).to(dev())
+        q = torch.randn(H, 1, d, generator=g).to(torch.bfloat16).to(dev())
+        kr, vr = ref.update(nk, nv, 0, {"head_lens": hl_r, "cu_klen": cu_r})
+        cu_r = cu_r + off
+        hl_r = hl_r + 1
+        ks, vs = slk.update(nk, nv, 0, {"head_lens": hl_s, "cu_klen": None})
+        hl_s += 1
+        cap = slk.cu_cap[0]
+        assert int(cap[-1]) == ks.shape[0] and torch.equal(hl_s, hl_r)
+        for h in range(H):
+            a, n = int(cap[h]), int(hl_s[h])
+            assert torch.equal(ks[a:a + n], kr[int(cu_r[h]):int(cu_r[h + 1])]), (step, h)
+            assert torch.equal(vs[a:a + n], vr[int(cu_r[h]):int(cu_r[h + 1])]), (step, h)
+        mx = int(hl_r.max())
+        want = flash_attn_varlen_func(q, kr.view(-1, 1, d), vr.view(-1, 1, d), cu_q, cu_r, 1, mx, causal=True)
+        got = _flash_attn_varlen_forward(q, ks.view(-1, 1, d), vs.view(-1, 1, d), cu_q, cap, 1, mx, 0.0, d ** -0.5, True,
+                                         seqused_k=hl_s)[0]
+        assert torch.equal(got, want), f"attention output differs at decode step {step}"
+
+
 # ------------------------------------------------------------------------------------------------
 # pool + top-k
 # ------------------------------------------------------------------------------------------------

@@ -217,3 +217,33 @@ def test_hooks_refuse_a_cache_without_layers():
         key_cache, value_cache = [], []
     with pytest.raises(TypeError, match="layered cache"):
         MP._layer_keys(OldCache(), 0)
+
+
+@pytest.mark.gpu
+def test_adakv_hook_decode_slack_equals_rebuild_path():
+    """config.kvc_decode_slack: the decode steps of AdaKV write their rows in place (re-layout every `slack` steps)
+    and attend over (segment starts, used lengths); same tokens and logits as the reference-style rebuild path."""
+    pytest.importorskip("flash_attn")
+    dev = torch.device("cuda:0")
+    model = tiny(dtype=torch.bfloat16, head_dim=128).to(dev)
+    kvc.replace_llama("adakv")
+    c = model.config
+    c.max_capacity_prompt, c.window_size, c.kernel_size, c.pooling, c.floor, c.normalize = 128, 32, 7, "maxpool", 0.2, True
+    ids = torch.randint(0, 97, (1, 700), generator=torch.Generator().manual_seed(4)).to(dev)
+    outs = []
+    for slack in (0, 3):
+        c.kvc_decode_slack = slack
+        for layer in model.model.layers:            # AdaKV clusters are built once per module: start afresh
+            if hasattr(layer.self_attn, "kv_cluster"):
+                del layer.self_attn.kv_cluster
+        out = model.generate(ids, max_new_tokens=11, do_sample=False, use_cache=True, return_dict_in_generate=True,
+                             output_logits=True)
+        torch.cuda.synchronize()
+        outs.append(out)
+        assert out.past_key_values._kvc_flat.slack == slack
+    assert torch.equal(outs[0].sequences, outs[1].sequences)
+    for a, b in zip(outs[0].logits, outs[1].logits):
+        assert torch.equal(a, b)
+    flat = outs[1].past_key_values._kvc_flat
+    lens = model.model.layers[0].self_attn.kv_cluster.head_lens
+    assert int(flat.cu_cap[0][-1]) == flat.key_cache[0].shape[0] >= int(lens.sum())
