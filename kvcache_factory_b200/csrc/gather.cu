@@ -24,7 +24,7 @@ gather_rows_kernel(RowSrc ksrc, RowSrc vsrc, const int32_t* __restrict__ idx, in
   tl_start(tl);
   const int unit = blockIdx.y;
   const int b = unit / Hq, h = unit % Hq;
-  const int nsel = kVarlen ? cap[h] : n_sel;
+  const int nsel = kVarlen ? min(cap[h], n_sel) : n_sel;   // varlen: n_sel = width of an index row (memory safety)
   const int rows = nsel + w;
   const int64_t out_row0 = kVarlen ? (int64_t)cu_klen[h] : (int64_t)unit * rows;
   const int rows_per_pass = kGatherThreads / chunks_per_row;
@@ -112,7 +112,7 @@ int gather_varlen(const void* k, int64_t k_sh, int64_t k_sl, const void* v, int6
   dim3 grid((rows + block_rows - 1) / block_rows, Hq);
   RowSrc ks{(const char*)k, 0, k_sh * e, k_sl * e}, vs{(const char*)v, 0, v_sh * e, v_sl * e};
   gather_rows_kernel<true><<<grid, kGatherThreads, 0, stream>>>(ks, vs, idx, idx_stride, cap, cu_klen, Hq, Hq / Hkv,
-                                                                 L, w, 0, cpr, (char*)out_k, (char*)out_v, KVC_TL_SLOT(2));
+                                                                 L, w, max_cap, cpr, (char*)out_k, (char*)out_v, KVC_TL_SLOT(2));
   return launch_status("gather_rows_kernel<varlen>");
 }
 

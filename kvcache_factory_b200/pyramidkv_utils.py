@@ -448,13 +448,28 @@ class AdaKVCluster:
                                       want_pooled=True, want_sums=True, sums_only=True)
         cap, head_lens, cu_klen = N.adakv_allocate(pooled.view(num_heads, n), sums, self.base_capacity,
                                                    self.floor_ratio, bool(self.normalize), w)
+        # Everything that depends on the capacities runs off DEVICE-side values with host-side upper bounds, so the
+        # select and the gather are already queued when the host reads the capacities (the reference syncs at the
+        # same point, :718): the read no longer sits between the kernels.
+        #   * per-head k: device tensor `cap`; the index buffer is k_ub wide (the cluster select covers k <= 8192)
+        #   * rows: sum_h cap_h <= H*base + H (round() moves each head by < 1), so H*(base + w) + H rows are allocated
+        #     and the exact prefix is returned
+        k_ub = min(n, 8192)
+        rows_ub = num_heads * (self.base_capacity + w) + num_heads
+        idx, _, _ = N.pool_topk(scores, self.kernel_size, self.pooling, k_ub, k_per_row=cap)
+        idx = idx.view(num_heads, k_ub)
+        flat_k, flat_v = N.gather_varlen(key_states, value_states, idx, cap, cu_klen, num_heads, w, k_ub, rows_ub)
         cap_host = cap.cpu()                                         # the reference syncs here too (:718)
         max_cap = int(cap_host.max())
         klen_sum = int(cap_host.sum()) + num_heads * w
-        idx, _, _ = N.pool_topk(scores, self.kernel_size, self.pooling, max_cap, k_per_row=cap)
-        idx = idx.view(num_heads, max_cap)
-        flat_k, flat_v = N.gather_varlen(key_states, value_states, idx, cap, cu_klen, num_heads, w, max_cap,
-                                         klen_sum)
+        if max_cap > k_ub:                                           # a head took more than the bound: exact width
+            idx, _, _ = N.pool_topk(scores, self.kernel_size, self.pooling, max_cap, k_per_row=cap)
+            idx = idx.view(num_heads, max_cap)
+            flat_k, flat_v = N.gather_varlen(key_states, value_states, idx, cap, cu_klen, num_heads, w, max_cap,
+                                             klen_sum)
+        else:
+            assert klen_sum <= rows_ub
+            flat_k, flat_v = flat_k[:klen_sum], flat_v[:klen_sum]
         self._init_metadata(device, num_heads, head_lens, cu_klen, klen_sum, max_cap + w)
         if self.keep_debug:
             self.debug = dict(scores=scores, pooled=pooled, cap=cap, indices=idx)
