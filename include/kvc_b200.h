@@ -133,6 +133,27 @@ int kvc_gather_dense(const void* k, int64_t k_sb, int64_t k_sh, int64_t k_sl,
                      int elem_bytes, void* out_k, void* out_v, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * One call for the whole dense update_kv of SnapKV / PyramidKV / StreamingLLM
+ * (pyramidkv/pyramidkv_utils.py:197-283, 306-347, 595-620): window scores -> pool + top-k -> gather +
+ * window, three launches on `stream` from ONE host call.  The eager drop-in path is launch bound
+ * (a layer of the reference's CPU-runnable config costs 22 us of GPU time and ~95 us of host time when
+ * every kernel is a separate Python -> ctypes round trip with its own allocations); this entry point
+ * carves scores, indices and the kernels' scratch out of one caller-provided workspace.
+ *
+ * pool == KVC_POOL_NONE with kernel_size == 0 means "no scoring at all": the first n_keep rows are kept
+ * (StreamingLLM).  out_idx / out_scores are written inside the workspace; their byte offsets are returned
+ * through idx_offset / scores_offset (may be NULL) for callers that want to inspect them.
+ * ---------------------------------------------------------------------------------------------- */
+size_t kvc_compress_dense_workspace_bytes(int B, int Hq, int Hkv, int L, int d, int w, int n_keep);
+int kvc_compress_dense(const void* q, int64_t q_sb, int64_t q_sh, int64_t q_sl,
+                       const void* k, int64_t k_sb, int64_t k_sh, int64_t k_sl,
+                       const void* v, int64_t v_sb, int64_t v_sh, int64_t v_sl,
+                       int B, int Hq, int Hkv, int L, int d, int w, int dtype,
+                       int kernel_size, int pool, int n_keep, int score_impl,
+                       void* out_k, void* out_v, void* workspace, size_t workspace_bytes,
+                       size_t* idx_offset, size_t* scores_offset, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Varlen (flattened) gather — replaces the per-head Python loop of AdaKVCluster.update_kv
  * pyramidkv/pyramidkv_utils.py:733-755: head h writes cap[h] selected rows then the w window rows
  * at row offset cu_klen[h] of the flattened [sum_h(cap[h]+w), d] cache.  Batch is 1 (:724).

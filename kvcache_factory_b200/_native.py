@@ -42,6 +42,10 @@ _SIGNATURES = {
     "kvc_pool_topk": (c_int, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _i64, _p, _p, _p, c_size_t, _p]),
     "kvc_gather_dense": (c_int, [_p, _i64, _i64, _i64, _p, _i64, _i64, _i64, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p,
                                  _p, _p]),
+    "kvc_compress_dense_workspace_bytes": (c_size_t, [_i] * 7),
+    "kvc_compress_dense": (c_int, [_p, _i64, _i64, _i64, _p, _i64, _i64, _i64, _p, _i64, _i64, _i64,
+                                   _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, c_size_t,
+                                   POINTER(c_size_t), POINTER(c_size_t), _p]),
     "kvc_gather_varlen": (c_int, [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p,
                                   _p, _p]),
     "kvc_adakv_allocate_workspace_bytes": (c_size_t, [_i] * 2),
@@ -260,6 +264,58 @@ def gather_dense(key_states: torch.Tensor, value_states: torch.Tensor, idx, num_
             idx.data_ptr() if idx is not None else None, B, num_heads, Hkv, L, d, n_sel, window_size, e,
             out_k.data_ptr(), out_v.data_ptr(), _stream(dev)))
     return out_k, out_v
+
+
+_ws_bytes_cache = {}
+
+
+def compress_dense(query_states: torch.Tensor, key_states: torch.Tensor, value_states: torch.Tensor, window_size: int,
+                   kernel_size: int, pooling, n_keep: int, num_heads: int, impl: int = IMPL_AUTO, seq_len: int = None,
+                   want_debug: bool = False):
+    """The whole dense update_kv in ONE library call: (K', V') [B,Hq,n_keep+w,d] (+ scores / indices views of the
+    workspace when ``want_debug``).  ``pooling == "streaming"`` keeps the first n_keep rows without scoring."""
+    dev = _require_cuda(key_states, value_states) if query_states is None else _require_cuda(query_states, key_states, value_states)
+    B, Hkv, L, d = key_states.shape
+    if value_states.shape != key_states.shape or value_states.dtype != key_states.dtype:
+        raise ValueError("key_states and value_states must have the same shape and dtype")
+    code = dtype_code(key_states.dtype)
+    e = key_states.element_size()
+    k = _rowmajor_last(key_states, 16 // e)
+    v = _rowmajor_last(value_states, 16 // e)
+    streaming = pooling == "streaming"
+    if streaming:
+        q, q_ptr, qs, pcode, ksz = None, None, (0, 0, 0), POOL_NONE, 0
+    else:
+        if query_states.dtype != key_states.dtype:
+            raise TypeError("query and key dtypes differ")
+        pcode, ksz = pool_code(pooling), kernel_size
+        q = _rowmajor_last(query_states, 8 if d == 128 else 2)
+        q_ptr, Lq = q.data_ptr(), q.shape[2]
+        if Lq != L:
+            if not (seq_len == L and Lq == window_size):
+                raise ValueError(f"query_states has {Lq} rows, key_states {L}")
+            q_ptr -= (L - window_size) * q.stride(2) * q.element_size()
+        qs = (q.stride(0), q.stride(1), q.stride(2))
+    out_k = torch.empty((B, num_heads, n_keep + window_size, d), dtype=k.dtype, device=dev)
+    out_v = torch.empty_like(out_k)
+    key = (dev.index, B, num_heads, Hkv, L, d, window_size, n_keep)
+    with torch.cuda.device(dev):
+        nbytes = _ws_bytes_cache.get(key)
+        if nbytes is None:
+            nbytes = _ws_bytes_cache[key] = max(256, lib().kvc_compress_dense_workspace_bytes(B, num_heads, Hkv, L, d, window_size, n_keep))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        io, so = c_size_t(0), c_size_t(0)
+        _check("kvc_compress_dense", lib().kvc_compress_dense(
+            q_ptr, qs[0], qs[1], qs[2], k.data_ptr(), k.stride(0), k.stride(1), k.stride(2),
+            v.data_ptr(), v.stride(0), v.stride(1), v.stride(2), B, num_heads, Hkv, L, d, window_size, code,
+            ksz, pcode, n_keep, impl, out_k.data_ptr(), out_v.data_ptr(), ws.data_ptr(), nbytes,
+            ctypes.byref(io), ctypes.byref(so), _stream(dev)))
+    if not want_debug or streaming:
+        return out_k, out_v, None, None
+    n = L - window_size
+    scores = ws[so.value: so.value + B * num_heads * n * e].view(key_states.dtype).view(B, num_heads, n)
+    idx = ws[io.value: io.value + B * num_heads * n_keep * 4].view(torch.int32).view(B, num_heads, n_keep)
+    return out_k, out_v, scores, idx
 
 
 def gather_varlen(key_states, value_states, idx, cap, cu_klen, num_heads: int, window_size: int, max_cap: int,

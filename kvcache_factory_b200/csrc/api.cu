@@ -236,6 +236,52 @@ int kvc_gather_dense(const void* k, int64_t k_sb, int64_t k_sh, int64_t k_sl, co
                       out_v, (cudaStream_t)stream);
 }
 
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+size_t kvc_compress_dense_workspace_bytes(int B, int Hq, int Hkv, int L, int d, int w, int n_keep) {
+  if (B <= 0 || Hq <= 0 || Hkv <= 0 || L <= w || w <= 0 || Hq % Hkv || n_keep < 0) return 0;
+  const size_t scores = align256((size_t)B * Hq * (L - w) * 2);
+  const size_t idx = align256((size_t)B * Hq * (n_keep > 0 ? n_keep : 1) * 4);
+  return scores + idx + align256(kvc_window_scores_workspace_bytes(B, Hq, Hkv, L, d, w)) +
+         align256(pool_topk_workspace_bytes(B * Hq, L - w, n_keep)) + 256;
+}
+
+int kvc_compress_dense(const void* q, int64_t q_sb, int64_t q_sh, int64_t q_sl, const void* k, int64_t k_sb,
+                       int64_t k_sh, int64_t k_sl, const void* v, int64_t v_sb, int64_t v_sh, int64_t v_sl, int B, int Hq,
+                       int Hkv, int L, int d, int w, int dtype, int kernel_size, int pool, int n_keep, int score_impl,
+                       void* out_k, void* out_v, void* workspace, size_t workspace_bytes, size_t* idx_offset,
+                       size_t* scores_offset, void* stream) {
+  if (int rc = check_device()) return rc;
+  if (int rc = check_shape(B, Hq, Hkv, L, d, w, dtype)) return rc;
+  KVC_REQUIRE(k && v && out_k && out_v && workspace, KVC_ERR_ARG, "null pointer argument");
+  KVC_REQUIRE(n_keep >= 0 && n_keep <= L - w, KVC_ERR_ARG, "n_keep=%d does not fit L-w=%d", n_keep, L - w);
+  const bool scored = !(pool == KVC_POOL_NONE && kernel_size == 0);
+  const int e = 2;
+  if (!scored)   // StreamingLLM: first n_keep rows + window, no index tensor at all
+    return kvc_gather_dense(k, k_sb, k_sh, k_sl, v, v_sb, v_sh, v_sl, nullptr, B, Hq, Hkv, L, d, n_keep, w, e, out_k, out_v, stream);
+  KVC_REQUIRE(q != nullptr, KVC_ERR_ARG, "null query pointer");
+  const size_t need = kvc_compress_dense_workspace_bytes(B, Hq, Hkv, L, d, w, n_keep);
+  KVC_REQUIRE(workspace_bytes >= need, KVC_ERR_WORKSPACE, "compress_dense workspace: have %zu need %zu", workspace_bytes, need);
+  char* ws = (char*)workspace;
+  const size_t scores_bytes = align256((size_t)B * Hq * (L - w) * 2);
+  const size_t idx_bytes = align256((size_t)B * Hq * (n_keep > 0 ? n_keep : 1) * 4);
+  const size_t sc_ws = align256(kvc_window_scores_workspace_bytes(B, Hq, Hkv, L, d, w));
+  const size_t sel_ws = align256(pool_topk_workspace_bytes(B * Hq, L - w, n_keep));
+  char* scores = ws;
+  int32_t* idx = (int32_t*)(ws + scores_bytes);
+  char* ws_scores = ws + scores_bytes + idx_bytes;
+  char* ws_select = ws_scores + sc_ws;
+  if (idx_offset) *idx_offset = scores_bytes;
+  if (scores_offset) *scores_offset = 0;
+  if (int rc = kvc_window_scores(q, q_sb, q_sh, q_sl, k, k_sb, k_sh, k_sl, B, Hq, Hkv, L, d, w, dtype, KVC_REDUCE_SUM, scores,
+                                 ws_scores, sc_ws > 256 ? sc_ws : 256, score_impl, stream))
+    return rc;
+  if (int rc = kvc_pool_topk(scores, B * Hq, L - w, dtype, kernel_size, pool, n_keep, nullptr, idx, n_keep, nullptr, nullptr,
+                             ws_select, sel_ws + 256, stream))
+    return rc;
+  return kvc_gather_dense(k, k_sb, k_sh, k_sl, v, v_sb, v_sh, v_sl, idx, B, Hq, Hkv, L, d, n_keep, w, e, out_k, out_v, stream);
+}
+
 int kvc_gather_varlen(const void* k, int64_t k_sh, int64_t k_sl, const void* v, int64_t v_sh, int64_t v_sl,
                       const int32_t* idx, int64_t idx_stride, const int32_t* cap, const int32_t* cu_klen, int Hq,
                       int Hkv, int L, int d, int w, int max_cap, int elem_bytes, void* out_k, void* out_v,

@@ -161,6 +161,7 @@ class _ScoredCluster:
     score_impl = N.IMPL_AUTO    # tests/bench may pin KVC_IMPL_MMA_SYNC or KVC_IMPL_TCGEN05
     async_tail = False          # run select + gather on the side stream (see wait_for_compression)
     async_scores = False        # with async_tail: also the scoring leaves the caller's stream (half-footprint kernel)
+    fused_call = True           # synchronous path: one C-ABI call per update_kv (kvc_compress_dense)
 
     def _configure(self, window_size, max_capacity_prompt, kernel_size, pooling, merge):
         self.window_size = window_size
@@ -200,6 +201,16 @@ class _ScoredCluster:
         w = self.window_size
         Hq = query_states.shape[1]
         score_stream = None
+        if scorer in ("window", "none") and not self.async_tail and not self.keep_debug and value_states.is_cuda \
+                and self.fused_call:
+            # synchronous drop-in default: score -> pool + top-k -> gather in ONE library call (three launches, one
+            # workspace): the eager path is launch bound, not GPU bound (22 us of kernels per cfg-1 layer)
+            if scorer == "window" and pooling not in ("avgpool", "maxpool"):
+                raise ValueError("Pooling method not supported")
+            kc, vc, _, _ = N.compress_dense(query_states if scorer == "window" else None, key_states, value_states, w,
+                                            self.kernel_size, pooling if scorer == "window" else "streaming", n_keep, Hq,
+                                            self.score_impl, seq_len=seq_len)
+            return kc, vc
         if scorer == "window":
             if pooling not in ("avgpool", "maxpool"):
                 raise ValueError("Pooling method not supported")
@@ -448,28 +459,16 @@ class AdaKVCluster:
                                       want_pooled=True, want_sums=True, sums_only=True)
         cap, head_lens, cu_klen = N.adakv_allocate(pooled.view(num_heads, n), sums, self.base_capacity,
                                                    self.floor_ratio, bool(self.normalize), w)
-        # Everything that depends on the capacities runs off DEVICE-side values with host-side upper bounds, so the
-        # select and the gather are already queued when the host reads the capacities (the reference syncs at the
-        # same point, :718): the read no longer sits between the kernels.
-        #   * per-head k: device tensor `cap`; the index buffer is k_ub wide (the cluster select covers k <= 8192)
-        #   * rows: sum_h cap_h <= H*base + H (round() moves each head by < 1), so H*(base + w) + H rows are allocated
-        #     and the exact prefix is returned
-        k_ub = min(n, 8192)
-        rows_ub = num_heads * (self.base_capacity + w) + num_heads
-        idx, _, _ = N.pool_topk(scores, self.kernel_size, self.pooling, k_ub, k_per_row=cap)
-        idx = idx.view(num_heads, k_ub)
-        flat_k, flat_v = N.gather_varlen(key_states, value_states, idx, cap, cu_klen, num_heads, w, k_ub, rows_ub)
         cap_host = cap.cpu()                                         # the reference syncs here too (:718)
         max_cap = int(cap_host.max())
         klen_sum = int(cap_host.sum()) + num_heads * w
-        if max_cap > k_ub:                                           # a head took more than the bound: exact width
-            idx, _, _ = N.pool_topk(scores, self.kernel_size, self.pooling, max_cap, k_per_row=cap)
-            idx = idx.view(num_heads, max_cap)
-            flat_k, flat_v = N.gather_varlen(key_states, value_states, idx, cap, cu_klen, num_heads, w, max_cap,
-                                             klen_sum)
-        else:
-            assert klen_sum <= rows_ub
-            flat_k, flat_v = flat_k[:klen_sum], flat_v[:klen_sum]
+        # (queuing this select + gather on device-side capacities with host-side upper bounds BEFORE the read was
+        # measured slower, 347 vs 316 us per cfg-4 layer: the 8192-wide select costs more than the sync it hides --
+        # the eager path is bound by host launch overhead, not by the read)
+        idx, _, _ = N.pool_topk(scores, self.kernel_size, self.pooling, max_cap, k_per_row=cap)
+        idx = idx.view(num_heads, max_cap)
+        flat_k, flat_v = N.gather_varlen(key_states, value_states, idx, cap, cu_klen, num_heads, w, max_cap,
+                                         klen_sum)
         self._init_metadata(device, num_heads, head_lens, cu_klen, klen_sum, max_cap + w)
         if self.keep_debug:
             self.debug = dict(scores=scores, pooled=pooled, cap=cap, indices=idx)

@@ -413,6 +413,39 @@ def test_pyramidkv_matches_reference_vectors(name, impl):
     _check_dense(PyramidKVCluster(**c["knobs"]), c, z, Q, K, V, impl)
 
 
+@pytest.mark.parametrize("method", ["snapkv", "pyramidkv", "streamingllm"])
+@pytest.mark.parametrize("layout", ["full_q", "window_q", "hf_transposed"])
+def test_fused_one_call_path_equals_three_calls(method, layout):
+    """kvc_compress_dense (the synchronous default: one library call per update_kv) launches the same three kernels as
+    the separate window_scores / pool_topk / gather_dense calls: identical bits, also from the HF tensor layouts."""
+    shape = Shape(2, 8, 2, 1777, 128)
+    w, cap = 32, 256
+    Q, K, V = make_qkv(shape, torch.bfloat16, layer_idx=5, dist="peaked", window=w)
+    Qd, Kd, Vd = Q.to(dev()), K.to(dev()), V.to(dev())
+    if layout == "hf_transposed":
+        Qd = Qd.transpose(1, 2).contiguous().transpose(1, 2)
+        Kd = Kd.transpose(1, 2).contiguous().transpose(1, 2)
+        Vd = Vd.transpose(1, 2).contiguous().transpose(1, 2)
+    mk = {"snapkv": lambda: SnapKVCluster(w, cap, 7, "avgpool"),
+          "pyramidkv": lambda: PyramidKVCluster(num_hidden_layers=8, window_size=w, max_capacity_prompt=cap, kernel_size=5,
+                                                pooling="maxpool", layer_idx=3),
+          "streamingllm": lambda: StreamingLLMKVCluster(w, cap)}[method]
+    a, b = mk(), mk()
+    b.fused_call = False
+    if layout == "window_q":
+        if method == "streamingllm":
+            pytest.skip("StreamingLLM reads no queries")
+        Ka, Va = a.update_kv_window(Kd, Qd[:, :, -w:].contiguous(), Vd, 4, shape.L)
+        Kb, Vb = b.update_kv_window(Kd, Qd[:, :, -w:].contiguous(), Vd, 4, shape.L)
+    else:
+        Ka, Va = a.update_kv(Kd, Qd, Vd, None, 4)
+        Kb, Vb = b.update_kv(Kd, Qd, Vd, None, 4)
+    torch.cuda.synchronize()
+    assert Ka.shape == Kb.shape and torch.equal(Ka, Kb) and torch.equal(Va, Vb)
+    with pytest.raises(ValueError, match="Pooling method not supported"):
+        SnapKVCluster(w, cap, 7, "medianpool").update_kv(Kd, Qd, Vd, None, 4)
+
+
 def test_repeated_layout_gives_same_result_as_unrepeated():
     shape = Shape(1, 8, 2, 600, 128)
     Q, K, V = make_qkv(shape, torch.bfloat16, layer_idx=4, dist="peaked", window=32)
