@@ -82,6 +82,20 @@ int kvc_window_scores(const void* q, int64_t q_sb, int64_t q_sh, int64_t q_sl,
                       void* workspace, size_t workspace_bytes, int impl, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Window scores from statistics the caller already has: `lse` is float32
+ * [B,Hq,w], the log-sum-exp (natural log, of the 1/sqrt(d)-scaled logits) of each observation-window query
+ * row over ALL keys with the causal mask inside the window -- exactly the `softmax_lse` rows the prefill's
+ * flash attention returns for the last w queries.  Only the second softmax pass runs (about half a scoring
+ * launch).  NOT bit-parity with the reference: flash attention's logits are not rounded to the model dtype
+ * before the softmax (pyramidkv_utils.py:317 rounds twice), so scores differ in the last bits; opt-in.
+ * Same workspace as kvc_window_scores.
+ * ---------------------------------------------------------------------------------------------- */
+int kvc_window_scores_lse(const void* q, int64_t q_sb, int64_t q_sh, int64_t q_sl,
+                          const void* k, int64_t k_sb, int64_t k_sh, int64_t k_sl, const float* lse,
+                          int B, int Hq, int Hkv, int L, int d, int w, int dtype, int reduce,
+                          void* out_scores, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * H2O scoring — replaces H2OKVCluster.update_kv pyramidkv/pyramidkv_utils.py:544-554: ALL L query
  * rows score every key (non-causal except the bottom-right w x w block), column-summed.  The
  * [B,H,L,L] matrix is never materialised.

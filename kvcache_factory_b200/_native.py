@@ -35,6 +35,8 @@ _SIGNATURES = {
     "kvc_window_scores_workspace_bytes": (c_size_t, [_i] * 6),
     "kvc_window_scores": (c_int, [_p, _i64, _i64, _i64, _p, _i64, _i64, _i64, _i, _i, _i, _i, _i, _i, _i, _i, _p,
                                   _p, c_size_t, _i, _p]),
+    "kvc_window_scores_lse": (c_int, [_p, _i64, _i64, _i64, _p, _i64, _i64, _i64, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p,
+                                      _p, c_size_t, _p]),
     "kvc_h2o_scores_workspace_bytes": (c_size_t, [_i] * 6),
     "kvc_h2o_scores": (c_int, [_p, _i64, _i64, _i64, _p, _i64, _i64, _i64, _i, _i, _i, _i, _i, _i, _i, _p, _p,
                                c_size_t, _p]),
@@ -135,7 +137,8 @@ def _rowmajor_last(t: torch.Tensor, align_elems: int) -> torch.Tensor:
 # op wrappers
 # ------------------------------------------------------------------------------------------------
 def window_scores(query_states: torch.Tensor, key_states: torch.Tensor, window_size: int,
-                  reduce: str = "sum", impl: int = IMPL_AUTO, seq_len: int = None) -> torch.Tensor:
+                  reduce: str = "sum", impl: int = IMPL_AUTO, seq_len: int = None,
+                  lse: torch.Tensor = None) -> torch.Tensor:
     """[B,Hq,L-w] scores of every non-window key under the last ``window_size`` queries.
 
     ``query_states`` is ``[B,Hq,L,d]`` or, with ``seq_len=L``, only its last ``window_size`` rows
@@ -156,6 +159,24 @@ def window_scores(query_states: torch.Tensor, key_states: torch.Tensor, window_s
             raise ValueError(f"query_states has {Lq} rows, key_states {L}")
         q_ptr -= (L - window_size) * q.stride(2) * q.element_size()
     out = torch.empty((B, Hq, L - window_size), dtype=key_states.dtype, device=dev)
+    if lse is not None:
+        # statistics supplied (float32 [B,Hq,w], e.g. flash attention's softmax_lse of the window rows): pass 2 only
+        _require_cuda(key_states, lse)
+        if lse.dtype != torch.float32 or tuple(lse.shape) != (B, Hq, window_size):
+            raise TypeError(f"lse must be float32 [B,Hq,w] = {(B, Hq, window_size)}, got {lse.dtype} {tuple(lse.shape)}")
+        lse = lse.contiguous()
+        q8 = _rowmajor_last(query_states, 8)
+        q_ptr = q8.data_ptr()
+        if Lq != L:
+            q_ptr -= (L - window_size) * q8.stride(2) * q8.element_size()
+        with torch.cuda.device(dev):
+            ws_bytes = lib().kvc_window_scores_workspace_bytes(B, Hq, Hkv, L, d, window_size)
+            ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=dev)
+            _check("kvc_window_scores_lse", lib().kvc_window_scores_lse(
+                q_ptr, q8.stride(0), q8.stride(1), q8.stride(2), k.data_ptr(), k.stride(0), k.stride(1), k.stride(2),
+                lse.data_ptr(), B, Hq, Hkv, L, d, window_size, code, REDUCE_MEAN if reduce == "mean" else REDUCE_SUM,
+                out.data_ptr(), ws.data_ptr(), ws.numel(), _stream(dev)))
+        return out
     with torch.cuda.device(dev):
         ws_bytes = lib().kvc_window_scores_workspace_bytes(B, Hq, Hkv, L, d, window_size)
         ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=dev)

@@ -28,7 +28,7 @@ bool window_scores_tc_supported(int B, int Hq, int Hkv, int L, int d, int w);
 bool window_scores_dyn_supported(int B, int Hq, int Hkv, int L, int d, int w);
 size_t window_scores_dyn_workspace_bytes(int B, int Hq, int Hkv, int L, int d, int w);
 int window_scores_dyn(const void*, int64_t, int64_t, int64_t, const void*, int64_t, int64_t, int64_t, int, int, int,
-                      int, int, int, int, int, void*, void*, size_t, cudaStream_t);
+                      int, int, int, int, int, void*, void*, size_t, const float*, cudaStream_t);
 bool window_scores_fused_supported(int B, int Hq, int Hkv, int L, int d, int w);
 size_t window_scores_fused_workspace_bytes(int B, int Hq, int Hkv, int L, int d, int w);
 int window_scores_fused(const void*, int64_t, int64_t, int64_t, const void*, int64_t, int64_t, int64_t, int, int, int,
@@ -178,12 +178,25 @@ int kvc_window_scores(const void* q, int64_t q_sb, int64_t q_sh, int64_t q_sl, c
                                workspace, workspace_bytes, impl == KVC_IMPL_TCGEN05_HALF, (cudaStream_t)stream);
   if (impl == KVC_IMPL_TCGEN05_DYN || (impl == KVC_IMPL_AUTO && dyn_ok && aligned))
     return window_scores_dyn(q, q_sb, q_sh, q_sl, k, k_sb, k_sh, k_sl, B, Hq, Hkv, L, d, w, dtype, reduce, out_scores,
-                             workspace, workspace_bytes, (cudaStream_t)stream);
+                             workspace, workspace_bytes, nullptr, (cudaStream_t)stream);
   if (impl == KVC_IMPL_TCGEN05 || (impl == KVC_IMPL_AUTO && tc_ok && aligned))
     return window_scores_tc(q, q_sb, q_sh, q_sl, k, k_sb, k_sh, k_sl, B, Hq, Hkv, L, d, w, dtype, reduce, out_scores,
                             workspace, workspace_bytes, (cudaStream_t)stream);
   return window_scores_mma(q, q_sb, q_sh, q_sl, k, k_sb, k_sh, k_sl, B, Hq, Hkv, L, d, w, dtype, reduce, out_scores,
                            workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int kvc_window_scores_lse(const void* q, int64_t q_sb, int64_t q_sh, int64_t q_sl, const void* k, int64_t k_sb,
+                          int64_t k_sh, int64_t k_sl, const float* lse, int B, int Hq, int Hkv, int L, int d, int w, int dtype,
+                          int reduce, void* out_scores, void* workspace, size_t workspace_bytes, void* stream) {
+  if (int rc = check_device()) return rc;
+  if (int rc = check_shape(B, Hq, Hkv, L, d, w, dtype)) return rc;
+  KVC_REQUIRE(q && k && lse && out_scores && workspace, KVC_ERR_ARG, "null pointer argument");
+  KVC_REQUIRE(reduce == KVC_REDUCE_SUM || reduce == KVC_REDUCE_MEAN, KVC_ERR_ARG, "bad reduce %d", reduce);
+  KVC_REQUIRE(window_scores_dyn_supported(B, Hq, Hkv, L, d, w), KVC_ERR_UNSUPPORTED,
+              "scores-from-LSE is implemented by the dynamic tcgen05 kernel only (d = 128, w in {8,16,32}, Hq/Hkv*w %% 32 == 0)");
+  return window_scores_dyn(q, q_sb, q_sh, q_sl, k, k_sb, k_sh, k_sl, B, Hq, Hkv, L, d, w, dtype, reduce, out_scores,
+                           workspace, workspace_bytes, lse, (cudaStream_t)stream);
 }
 
 size_t kvc_h2o_scores_workspace_bytes(int B, int Hq, int Hkv, int L, int d, int w) {

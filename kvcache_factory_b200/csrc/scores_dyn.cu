@@ -67,7 +67,10 @@ struct Params {
   int max_chunks;       // partial slots per unit in `stats`
   float scale;
   int reduce_mean;
+  int stagger_ns;       // see the epilogue: nanoseconds between the warpgroups' restarts after a CTA-wide sync
   float2* stats;        // [units][max_chunks][128]
+  const float* lse;     // optional [B,Hq,w]: log-sum-exp of every window query row over all keys (natural log, scaled
+                        // logits), e.g. the softmax_lse the prefill's flash attention returns: pass 1 is skipped
   uint16_t* out;        // [B,Hq,L-w]
   unsigned long long* tl;
 };
@@ -95,8 +98,16 @@ __device__ __forceinline__ void dstamp(int slot, long long v = -1) {
   g_dtrace[blockIdx.x * 8 + slot] = v >= 0 ? v : t;
 }
 #define DYN_STAMP(cond, ...) do { if (cond) dstamp(__VA_ARGS__); } while (0)
+// CTA 0, the four epilogue warps of SM sub-partition 2 (warps 2, 6, 10, 14: one per warpgroup), first 64 tiles:
+// SM-clock stamps {accumulator seen, columns loaded, math done, ring code}
+__device__ unsigned g_wtrace[4][64][4];
+__device__ __forceinline__ void wstamp(int wg, unsigned ts, int slot, unsigned v = 0xffffffffu) {
+  if (blockIdx.x == 0 && ts < 64) g_wtrace[wg][ts][slot] = v != 0xffffffffu ? v : (unsigned)clock64();
+}
+#define DYN_WSTAMP(...) do { if ((threadIdx.x & 127) == 64 && (threadIdx.x >> 5) >= 2) wstamp(__VA_ARGS__); } while (0)
 #else
 #define DYN_STAMP(cond, ...) do { } while (0)
+#define DYN_WSTAMP(...) do { } while (0)
 #endif
 
 __device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
@@ -190,18 +201,18 @@ window_score_dyn_kernel(const __grid_constant__ CUtensorMap tmap_k, const Params
       for (int t = t0; t < t1; ++t) emit(v, 0, t, t == t1 - 1, j);
     };
     // regular pass-1 work: one chunk of x, one of y (both claims in flight together)
-    unsigned c0 = 0, c1 = 0;
-    if (lane == 0) {
+    unsigned c0 = 0xffffffffu, c1 = 0xffffffffu;
+    if (lane == 0 && p.lse == nullptr) {
       c0 = atomicAdd(&ctl->p1_next[unit_0], 1u);
       if (nvis == 2) c1 = atomicAdd(&ctl->p1_next[unit_1], 1u);
     }
     c0 = __shfl_sync(0xffffffffu, c0, 0);
     c1 = __shfl_sync(0xffffffffu, c1, 0);
-    if ((int)c0 < n1c_0) emit_chunk(0, (int)c0);
-    if (nvis == 2 && (int)c1 < n1c_1) emit_chunk(1, (int)c1);
+    if (c0 < (unsigned)n1c_0) emit_chunk(0, (int)c0);
+    if (nvis == 2 && c1 < (unsigned)n1c_1) emit_chunk(1, (int)c1);
     // leftovers (chunks whose natural owner is not running yet) + the first pass-2 claim, all in flight together
     unsigned p2c = 0;
-    for (;;) {
+    for (; p.lse == nullptr;) {
       unsigned l0 = 0, l1 = 0;
       if (lane == 0) {
         l0 = atomicAdd(&ctl->p1_next[unit_0], 1u);
@@ -303,6 +314,7 @@ window_score_dyn_kernel(const __grid_constant__ CUtensorMap tmap_k, const Params
     constexpr int kHeadsPerChunk = 32 / W;
     bool folded_0 = false, folded_1 = false;
     int n1_tiles = 0, n2_tiles = 0, npub = 0;
+    bool restagger = true;
 
     for (unsigned ts = 0;; ++ts) {
       const int buf = ts % kNumBuf;
@@ -310,6 +322,12 @@ window_score_dyn_kernel(const __grid_constant__ CUtensorMap tmap_k, const Params
       tc_fence_after();
       const int code = ring[ts % kRing].x;
       DYN_STAMP(et == 0 && ts == 0, 1);
+      DYN_WSTAMP(wg, ts, 0);
+      DYN_WSTAMP(wg, ts, 3, (unsigned)code);
+      if (restagger) {
+        restagger = false;
+        if (wg > 0 && p.stagger_ns > 0) __nanosleep(wg * p.stagger_ns);
+      }
       if (code < 0) break;
       const int tile = code & kTileMask;
       const int v = (code & kVisitBit) ? 1 : 0;
@@ -326,6 +344,7 @@ window_score_dyn_kernel(const __grid_constant__ CUtensorMap tmap_k, const Params
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty(buf));
+          DYN_WSTAMP(wg, ts, 1);
           if (key0 + 32 > nscore) {  // chunk touches the w x w causal block or the ragged end
             const int rg = VSEL(ublk, v) * 128 + r_loc;
             const int last_key = min(p.L - 1, rg / W < p.groups ? nscore + rg % W : p.L - 1);
@@ -335,6 +354,7 @@ window_score_dyn_kernel(const __grid_constant__ CUtensorMap tmap_k, const Params
           }
         }
         ++n1_tiles;
+        if (zacc[0].x >= 0.f) DYN_WSTAMP(wg, ts, 2);
         if (code & kLastBit) {
           // ---- end of a chunk: combine the four column slices (fixed order), publish the partial ----
           const int chunk = ring[ts % kRing].y;
@@ -360,6 +380,7 @@ window_score_dyn_kernel(const __grid_constant__ CUtensorMap tmap_k, const Params
           for (int a = 0; a < 4; ++a) zacc[a] = make_float2(0.f, 0.f);
           DYN_STAMP(et == 0 && npub < 2, 2 + npub);
           ++npub;
+          restagger = true;
         }
       } else {
         // ---------------- pass 2: thread <-> key, columns are the stacked query rows ----------------
@@ -368,6 +389,15 @@ window_score_dyn_kernel(const __grid_constant__ CUtensorMap tmap_k, const Params
           // claimed by a RUNNING CTA before any pass-2 tile of it could be claimed, and those CTAs publish without
           // waiting for anybody: this wait always ends (normally it does not wait at all, see the header).
           if (v) folded_1 = true; else folded_0 = true;
+          if (p.lse != nullptr) {
+            // statistics supplied by the caller: c_row = -lse * log2(e); no pass 1, nothing to wait for
+            if (et < 128) {
+              const int rg = VSEL(ublk, v) * 128 + et, hl = rg / W, i = rg % W;
+              crow[v * 128 + et] = hl < p.groups
+                  ? -p.lse[((int64_t)VSEL(ub, v) * p.Hq + VSEL(ukvh, v) * p.groups + hl) * p.w + i] * kLog2e : -INFINITY;
+            }
+            epi_sync();
+          } else {
           if (et == 0) {
             for (unsigned spin = 0; ld_acquire_u32(&ctl->done[VSEL(unit, v)]) < (unsigned)VSEL(n1c, v); ++spin) {
               __nanosleep(40);
@@ -415,7 +445,9 @@ window_score_dyn_kernel(const __grid_constant__ CUtensorMap tmap_k, const Params
             crow[v * 128 + et] = ((VSEL(ublk, v) * 128 + et) / W < p.groups) ? (-mx * kLog2e - log2f(z)) : -INFINITY;
           }
           epi_sync();
+          }
           DYN_STAMP(et == 0, 4 + v);
+          if (wg > 0 && p.stagger_ns > 0) __nanosleep(wg * p.stagger_ns);
         }
         const int key = tile * kTile + r_loc;
         const int head0 = (VSEL(ublk, v) * 128 + wg * 32) / W;
@@ -429,6 +461,7 @@ window_score_dyn_kernel(const __grid_constant__ CUtensorMap tmap_k, const Params
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty(buf));
+          DYN_WSTAMP(wg, ts, 1);
           float2 acc[kHeadsPerChunk];
 #pragma unroll
           for (int h = 0; h < kHeadsPerChunk; ++h) acc[h] = make_float2(0.f, 0.f);
@@ -446,6 +479,7 @@ window_score_dyn_kernel(const __grid_constant__ CUtensorMap tmap_k, const Params
           }
         }
         ++n2_tiles;
+        DYN_WSTAMP(wg, ts, 2);
       }
     }
     DYN_STAMP(et == 0, 6);
@@ -556,6 +590,9 @@ static int dispatch_w(const CUtensorMap& tmap, const Params& sp, const Plan& pl,
 extern "C" int kvc_debug_dyn_trace(long long* out, int n) {
   return (int)cudaMemcpyFromSymbol(out, dyn::g_dtrace, sizeof(long long) * (size_t)n);
 }
+extern "C" int kvc_debug_dyn_warp_trace(unsigned* out) {
+  return (int)cudaMemcpyFromSymbol(out, dyn::g_wtrace, sizeof(unsigned) * 4 * 64 * 4);
+}
 #endif
 
 bool window_scores_tc_supported(int B, int Hq, int Hkv, int L, int d, int w);
@@ -577,7 +614,7 @@ size_t window_scores_dyn_workspace_bytes(int B, int Hq, int Hkv, int L, int d, i
 
 int window_scores_dyn(const void* q, int64_t q_sb, int64_t q_sh, int64_t q_sl, const void* k, int64_t k_sb,
                       int64_t k_sh, int64_t k_sl, int B, int Hq, int Hkv, int L, int d, int w, int dtype, int reduce,
-                      void* out_scores, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+                      void* out_scores, void* workspace, size_t workspace_bytes, const float* lse, cudaStream_t stream) {
   using namespace dyn;
   KVC_REQUIRE(window_scores_dyn_supported(B, Hq, Hkv, L, d, w), KVC_ERR_UNSUPPORTED,
               "dynamic tcgen05 scoring kernel does not cover this shape (Hq/Hkv=%d, w=%d, d=%d, B*Hkv=%d)", Hq / Hkv, w, d,
@@ -597,7 +634,10 @@ int window_scores_dyn(const void* q, int64_t q_sb, int64_t q_sh, int64_t q_sl, c
   sp.nblk = pl.nblk; sp.units = pl.units; sp.nx = pl.nx; sp.ny = pl.ny; sp.max_chunks = pl.max_chunks;
   sp.scale = 1.0f / sqrtf((float)d);
   sp.reduce_mean = reduce == KVC_REDUCE_MEAN;
+  static const int stagger = [] { const char* e = getenv("KVC_DYN_STAGGER_NS"); return e ? atoi(e) : 0; }();
+  sp.stagger_ns = stagger;
   sp.stats = (float2*)workspace;
+  sp.lse = lse;
   sp.out = (uint16_t*)out_scores;
   sp.tl = KVC_TL_SLOT(0);
   return dtype == KVC_BF16 ? dispatch_w<Bf16>(tmap, sp, pl, stream) : dispatch_w<Fp16>(tmap, sp, pl, stream);

@@ -141,6 +141,22 @@ def _make_forward(method: str, family):
             _init_cluster(self, method)
             self.kv_seq_len = q_len                                   # llama_model.py:362-376
             k_att, v_att = key_states, value_states                   # attention sees the whole prompt
+            lse_kw = {}
+            if method in ("snapkv", "pyramidkv") and getattr(self.config, "kvc_scores_from_lse", False) \
+                    and query_states.is_cuda and query_states.dtype in (torch.bfloat16, torch.float16) \
+                    and q_len >= getattr(self.kv_cluster, "max_capacity_prompt", 1 << 62):
+                # SURVEY.md section 8 f4 (opt-in, config.kvc_scores_from_lse): the prefill runs through flash attention
+                # directly, which hands back the log-sum-exp of every query row; the observation window's rows replace
+                # the first softmax pass of the scoring kernel
+                from flash_attn import flash_attn_func
+                fa_out, fa_lse, _ = flash_attn_func(query_states.transpose(1, 2), key_states.transpose(1, 2),
+                                                    value_states.transpose(1, 2), dropout_p=0.0, softmax_scale=self.scaling,
+                                                    causal=True, return_attn_probs=True)
+                lse_kw = dict(window_lse=fa_lse[:, :, -self.kv_cluster.window_size:].float().contiguous())
+                kc, vc = self.kv_cluster.update_kv(key_states, query_states, value_states, attention_mask,
+                                                   self.num_key_value_groups, **lse_kw)
+                _store_prefill(past_key_values, kc, vc, self.layer_idx, getattr(self.kv_cluster, "async_tail", False))
+                return self.o_proj(fa_out.reshape(*input_shape, -1).contiguous()), None
             kc, vc = self.kv_cluster.update_kv(key_states, query_states, value_states, attention_mask,
                                                self.num_key_value_groups)
             _store_prefill(past_key_values, kc, vc, self.layer_idx, getattr(self.kv_cluster, "async_tail", False))

@@ -177,7 +177,8 @@ class _ScoredCluster:
             return None
         return self.max_capacity_prompt - self.window_size
 
-    def update_kv_window(self, key_states, query_window, value_states, num_key_value_groups, seq_len=None):
+    def update_kv_window(self, key_states, query_window, value_states, num_key_value_groups, seq_len=None,
+                         window_lse=None):
         """``update_kv`` for callers that hold only the observation window of the queries.
 
         ``query_window`` is ``[B,Hq,window_size,d]`` (the last ``window_size`` rows of
@@ -191,18 +192,23 @@ class _ScoredCluster:
         if n_keep is None:
             return key_states, value_states
         return self._compress(key_states, query_window, value_states, n_keep, scorer=self._scorer,
-                              pooling=self.pooling if self._scorer == "window" else None, seq_len=q_len)
+                              pooling=self.pooling if self._scorer == "window" else None, seq_len=q_len,
+                              window_lse=window_lse)
 
     _scorer = "window"
 
     def _compress(self, key_states, query_states, value_states, n_keep: int, *, scorer: str,
-                  pooling, seq_len=None) -> Tuple[torch.Tensor, torch.Tensor]:
+                  pooling, seq_len=None, window_lse=None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """``window_lse`` (float32 ``[B,Hq,w]``, optional, not in the reference): log-sum-exp of the observation-window
+        query rows over all keys, as the prefill's flash attention returns it (``softmax_lse[..., -w:]``).  The first
+        softmax pass is then skipped.  Flash attention does not round its logits to the model
+        dtype, so the scores differ from the reference's in the last bits: opt-in, not parity mode."""
         _check_merge(self.merge)
         w = self.window_size
         Hq = query_states.shape[1]
         score_stream = None
         if scorer in ("window", "none") and not self.async_tail and not self.keep_debug and value_states.is_cuda \
-                and self.fused_call:
+                and self.fused_call and window_lse is None:
             # synchronous drop-in default: score -> pool + top-k -> gather in ONE library call (three launches, one
             # workspace): the eager path is launch bound, not GPU bound (22 us of kernels per cfg-1 layer)
             if scorer == "window" and pooling not in ("avgpool", "maxpool"):
@@ -215,7 +221,7 @@ class _ScoredCluster:
             if pooling not in ("avgpool", "maxpool"):
                 raise ValueError("Pooling method not supported")
             if self.async_tail and self.async_scores and (Hq // key_states.shape[1]) * w <= 128 and w <= 32 \
-                    and key_states.shape[-1] == 128:
+                    and key_states.shape[-1] == 128 and window_lse is None:
                 # fully asynchronous: the scoring goes to one of two rotating streams as the half-footprint
                 # kernel, so that the scoring launches of consecutive calls share every SM and fill each
                 # other's prologue / grid-barrier / tail gaps (29.4 vs 34.6 us per cfg-2 layer)
@@ -236,7 +242,8 @@ class _ScoredCluster:
                     for t in (query_states, key_states):
                         t.record_stream(score_stream)
             else:
-                scores = N.window_scores(query_states, key_states, w, "sum", self.score_impl, seq_len=seq_len)
+                scores = N.window_scores(query_states, key_states, w, "sum", self.score_impl, seq_len=seq_len,
+                                         lse=window_lse)
         elif scorer == "h2o":
             scores = N.h2o_scores(query_states, key_states, w)
         else:
@@ -289,7 +296,7 @@ class SnapKVCluster(_ScoredCluster):
     def reset(self, window_size=64, max_capacity_prompt=256 + 64, kernel_size=5, pooling='avgpool', merge=None):
         self._configure(window_size, max_capacity_prompt, kernel_size, pooling, merge)
 
-    def update_kv(self, key_states, query_states, value_states, attention_mask, num_key_value_groups):
+    def update_kv(self, key_states, query_states, value_states, attention_mask, num_key_value_groups, window_lse=None):
         assert key_states.shape[-2] == query_states.shape[-2]        # prefill only (:309)
         q_len = query_states.shape[-2]
         _kv_heads(key_states, query_states, num_key_value_groups)
@@ -297,7 +304,8 @@ class SnapKVCluster(_ScoredCluster):
         if q_len < self.max_capacity_prompt:
             return key_states, value_states                          # same objects (:314-315)
         return self._compress(key_states, query_states, value_states,
-                              self.max_capacity_prompt - self.window_size, scorer="window", pooling=self.pooling)
+                              self.max_capacity_prompt - self.window_size, scorer="window", pooling=self.pooling,
+                              window_lse=window_lse)
 
 
 class PyramidKVCluster(_ScoredCluster):
@@ -324,7 +332,7 @@ class PyramidKVCluster(_ScoredCluster):
             return None                                              # :218-219
         return base if q_len < base * 2 else self.layer_budget(q_len)  # :220 / :252
 
-    def update_kv(self, key_states, query_states, value_states, attention_mask, num_key_value_groups):
+    def update_kv(self, key_states, query_states, value_states, attention_mask, num_key_value_groups, window_lse=None):
         assert key_states.shape[-2] == query_states.shape[-2]        # :200
         q_len = query_states.shape[-2]
         _kv_heads(key_states, query_states, num_key_value_groups)
@@ -335,7 +343,7 @@ class PyramidKVCluster(_ScoredCluster):
             return key_states, value_states                          # :218-219
         n_keep = base if q_len < base * 2 else budget                # :220 / :252
         return self._compress(key_states, query_states, value_states, n_keep, scorer="window",
-                              pooling=self.pooling)
+                              pooling=self.pooling, window_lse=window_lse)
 
 
 class H2OKVCluster(_ScoredCluster):

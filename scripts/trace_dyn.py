@@ -30,6 +30,19 @@ print("pass-1 tiles per CTA: min %d max %d sum %d;  pass-2: min %d max %d sum %d
 for c in (0, 1, 8, 70, 147):
     print("cta", c, [(x - t0) if x > 1000 else x for x in t[c]])
 
+if hasattr(raw, "kvc_debug_dyn_warp_trace"):
+    wb = (ctypes.c_uint * (4 * 64 * 4))()
+    raw.kvc_debug_dyn_warp_trace(wb)
+    base = min(wb[(g * 64 + 0) * 4 + 0] for g in range(4))
+    print("--- CTA 0, the four epilogue warps of one SM sub-partition (one per warpgroup): per tile, SM cycles: seen loaded done  (x4 warpgroups)")
+    for j in range(34):
+        row = []
+        for g in range(4):
+            r = [wb[(g * 64 + j) * 4 + k] for k in range(4)]
+            row.append(" ".join(f"{(x - base) & 0xffffffff:6d}" for x in r[:3]))
+        code = wb[(0 * 64 + j) * 4 + 3]
+        kind = "stop" if code == 0xffffffff else ("P2" if code & (1 << 27) else "P1") + (".y" if code & (1 << 26) else ".x")
+        print(f"  {j:2d} {kind:5s} | " + " | ".join(row))
 if not hasattr(raw, "kvc_debug_dyn_tile_trace"):
     sys.exit(0)          # the per-tile stamps exist only in experimental builds of scores_dyn.cu
 tb = (ctypes.c_uint * (2 * 64 * 8))()

@@ -661,3 +661,58 @@ def test_scoring_implementations_agree_on_random_shapes():
             assert (a == b).mean() > 0.99, (trial, shape, w, impl)
             checked += 1
     assert checked >= 55
+
+
+# ------------------------------------------------------------------------------------------------
+# f4: window scores from supplied statistics (log-sum-exp of the window rows), pass 2 only
+# ------------------------------------------------------------------------------------------------
+LSE_CASES = [(1, 8, 2, 777, 32), (2, 4, 4, 400, 8), (1, 16, 2, 1500, 32), (1, 32, 8, 4096, 32), (1, 32, 8, 2048, 16)]
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("case", LSE_CASES, ids=lambda c: "B%d_Hq%d_Hkv%d_L%d_w%d" % c)
+def test_window_scores_from_exact_lse_match_two_pass_kernel(dtype, case):
+    """With the log-sum-exp of the reference's OWN (dtype-rounded) logits the pass-2-only kernel must reproduce the
+    two-pass scores: c_row = -lse*log2e instead of -M*log2e - log2 Z, i.e. the same number up to fp32 rounding."""
+    B, Hq, Hkv, L, w = case
+    shape = Shape(B, Hq, Hkv, L, 128)
+    Q, K, _ = make_qkv(shape, dtype, layer_idx=2, dist="peaked", window=w)
+    Kr = O.repeat_kv(K, Hq // Hkv)
+    logits = torch.matmul(Q[..., -w:, :], Kr.transpose(2, 3)) / (128 ** 0.5)
+    logits[:, :, -w:, -w:] += O._block_causal_bias(w, logits.dtype)[None, None]
+    lse = torch.logsumexp(logits.float(), dim=-1)                      # [B,Hq,w]
+    ref = O.window_scores(Kr, Q, w, "sum")
+    got = _native.window_scores(Q.to(dev()), K.to(dev()), w, "sum", lse=lse.to(dev()))
+    torch.cuda.synchronize()
+    bad, worst = score_mismatch(got, ref, dtype, SCORE_ULPS)
+    exact = float((got.cpu() == ref).float().mean())
+    assert bad == 0.0, f"{bad:.2%} of scores off by more than {SCORE_ULPS} ulps (worst {worst:.1f}x)"
+    assert exact >= SCORE_EXACT_FRAC, f"only {exact:.2%} of scores bit-identical to the oracle"
+    # window-only queries take the same path
+    got_w = _native.window_scores(Q[:, :, -w:].contiguous().to(dev()), K.to(dev()), w, "sum", seq_len=L, lse=lse.to(dev()))
+    assert torch.equal(got, got_w)
+
+
+def test_window_scores_from_flash_attention_lse():
+    """The intended source: softmax_lse of the prefill's flash attention.  Its logits are NOT rounded to the model dtype,
+    so this is an approximation of the reference (stated tolerance: scores within 2 % relative or 1e-4 absolute, top-k
+    sets >= 97 % identical), not parity."""
+    flash_attn = pytest.importorskip("flash_attn")
+    shape = Shape(1, 32, 8, 8192, 128)
+    w, cap = 32, 1024
+    Q, K, V = make_qkv(shape, torch.bfloat16, layer_idx=8, dist="peaked", window=w)
+    Qd, Kd, Vd = Q.to(dev()), K.to(dev()), V.to(dev())
+    _, lse, _ = flash_attn.flash_attn_func(Qd.transpose(1, 2), Kd.transpose(1, 2), Vd.transpose(1, 2), causal=True,
+                                           return_attn_probs=True)
+    wl = lse[:, :, -w:].float().contiguous()
+    a = SnapKVCluster(w, cap, 7, "avgpool"); a.keep_debug = True
+    b = SnapKVCluster(w, cap, 7, "avgpool"); b.keep_debug = True
+    Ka, Va = a.update_kv(Kd, Qd, Vd, None, 4)
+    Kb, Vb = b.update_kv(Kd, Qd, Vd, None, 4, window_lse=wl)
+    torch.cuda.synchronize()
+    sa, sb = a.debug["scores"].float(), b.debug["scores"].float()
+    assert bool(((sa - sb).abs() <= 0.02 * sa.abs() + 1e-4).all())
+    ia, ib = a.debug["indices"].cpu(), b.debug["indices"].cpu()
+    agree = np.mean([len(set(ia[0, h].tolist()) & set(ib[0, h].tolist())) / (cap - w) for h in range(32)])
+    assert agree >= 0.97, agree
+    assert Kb.shape == Ka.shape and torch.equal(Kb[:, :, -w:], Ka[:, :, -w:])

@@ -4,6 +4,7 @@ CPU tests drive the hook logic with an ORACLE-backed cluster (the product cluste
 the GPU test runs the real CUDA path inside a tiny random Llama and checks the cached rows against
 the oracle applied to the tensors the hook handed to ``update_kv``.
 """
+import numpy as np
 import pytest
 import torch
 
@@ -247,3 +248,28 @@ def test_adakv_hook_decode_slack_equals_rebuild_path():
     flat = outs[1].past_key_values._kvc_flat
     lens = model.model.layers[0].self_attn.kv_cluster.head_lens
     assert int(flat.cu_cap[0][-1]) == flat.key_cache[0].shape[0] >= int(lens.sum())
+
+
+@pytest.mark.gpu
+def test_scores_from_lse_through_the_hooks():
+    """config.kvc_scores_from_lse: the prefill attention runs through flash attention, whose log-sum-exp replaces the
+    first softmax pass of the scoring kernel; the cache has the same shape and (nearly) the same rows."""
+    pytest.importorskip("flash_attn")
+    dev = torch.device("cuda:0")
+    model = tiny(dtype=torch.bfloat16, head_dim=128, layers=2).to(dev)
+    kvc.replace_llama("snapkv")
+    model.config.max_capacity_prompt, model.config.window_size, model.config.kernel_size = 256, 32, 7
+    model.config.pooling = "avgpool"
+    ids = torch.randint(0, 97, (1, 2000), generator=torch.Generator().manual_seed(6)).to(dev)
+    caches = []
+    for flag in (False, True):
+        model.config.kvc_scores_from_lse = flag
+        out = model.generate(ids, max_new_tokens=3, do_sample=False, use_cache=True, return_dict_in_generate=True)
+        torch.cuda.synchronize()
+        caches.append(out.past_key_values.layers[0].keys[:, :, :256].cpu())
+        assert out.sequences.shape == (1, 2003)
+    a, b = caches
+    assert a.shape == b.shape == (1, 4, 256, 128)
+    same_rows = np.mean([len({tuple(r.tolist()[:4]) for r in a[0, h]} & {tuple(r.tolist()[:4]) for r in b[0, h]}) / 256
+                         for h in range(4)])
+    assert same_rows > 0.9, same_rows
