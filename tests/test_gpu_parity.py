@@ -666,7 +666,7 @@ def test_scoring_implementations_agree_on_random_shapes():
 # ------------------------------------------------------------------------------------------------
 # f4: window scores from supplied statistics (log-sum-exp of the window rows), pass 2 only
 # ------------------------------------------------------------------------------------------------
-LSE_CASES = [(1, 8, 2, 777, 32), (2, 4, 4, 400, 8), (1, 16, 2, 1500, 32), (1, 32, 8, 4096, 32), (1, 32, 8, 2048, 16)]
+LSE_CASES = [(1, 8, 2, 777, 32), (2, 32, 8, 400, 8), (1, 16, 2, 1500, 32), (1, 32, 8, 4096, 32), (1, 32, 8, 2048, 16)]
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
