@@ -147,6 +147,15 @@ int kvc_gather_dense(const void* k, int64_t k_sb, int64_t k_sh, int64_t k_sl,
                      int elem_bytes, void* out_k, void* out_v, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * L2Norm policy (pyramidkv/pyramidkv_utils.py:394-429): selection scores from the
+ * key norms alone.  out[b, hq, l] = -||K[b, hq / (Hq/Hkv), l, :]||_2 in the model dtype [B,Hq,L] (negated:
+ * kvc_pool_topk(pool = NONE) then returns the `cap` smallest norms in ascending order, the reference's
+ * argsort()[:cap]); follow with kvc_gather_dense(w = 0).
+ * ---------------------------------------------------------------------------------------------- */
+int kvc_key_norm_scores(const void* k, int64_t k_sb, int64_t k_sh, int64_t k_sl,
+                        int B, int Hq, int Hkv, int L, int d, int dtype, void* out_scores, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * One call for the whole dense update_kv of SnapKV / PyramidKV / StreamingLLM
  * (pyramidkv/pyramidkv_utils.py:197-283, 306-347, 595-620): window scores -> pool + top-k -> gather +
  * window, three launches on `stream` from ONE host call.  The eager drop-in path is launch bound

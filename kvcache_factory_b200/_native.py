@@ -44,6 +44,7 @@ _SIGNATURES = {
     "kvc_pool_topk": (c_int, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _i64, _p, _p, _p, c_size_t, _p]),
     "kvc_gather_dense": (c_int, [_p, _i64, _i64, _i64, _p, _i64, _i64, _i64, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p,
                                  _p, _p]),
+    "kvc_key_norm_scores": (c_int, [_p, _i64, _i64, _i64, _i, _i, _i, _i, _i, _i, _p, _p]),
     "kvc_compress_dense_workspace_bytes": (c_size_t, [_i] * 7),
     "kvc_compress_dense": (c_int, [_p, _i64, _i64, _i64, _p, _i64, _i64, _i64, _p, _i64, _i64, _i64,
                                    _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, c_size_t,
@@ -285,6 +286,20 @@ def gather_dense(key_states: torch.Tensor, value_states: torch.Tensor, idx, num_
             idx.data_ptr() if idx is not None else None, B, num_heads, Hkv, L, d, n_sel, window_size, e,
             out_k.data_ptr(), out_v.data_ptr(), _stream(dev)))
     return out_k, out_v
+
+
+def key_norm_scores(key_states: torch.Tensor, num_heads: int) -> torch.Tensor:
+    """[B,Hq,L] NEGATED key L2 norms in the model dtype (L2Norm policy: top-k of this = smallest norms, ascending)."""
+    dev = _require_cuda(key_states)
+    B, Hkv, L, d = key_states.shape
+    code = dtype_code(key_states.dtype)
+    k = _rowmajor_last(key_states, 8)
+    out = torch.empty((B, num_heads, L), dtype=key_states.dtype, device=dev)
+    with torch.cuda.device(dev):
+        _check("kvc_key_norm_scores", lib().kvc_key_norm_scores(
+            k.data_ptr(), k.stride(0), k.stride(1), k.stride(2), B, num_heads, Hkv, L, d, code, out.data_ptr(),
+            _stream(dev)))
+    return out
 
 
 _ws_bytes_cache = {}

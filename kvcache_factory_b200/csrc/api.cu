@@ -13,6 +13,7 @@ int gather_dense(const void*, int64_t, int64_t, int64_t, const void*, int64_t, i
                  int, int, int, int, int, int, int, void*, void*, cudaStream_t);
 int gather_varlen(const void*, int64_t, int64_t, const void*, int64_t, int64_t, const int32_t*, int64_t,
                   const int32_t*, const int32_t*, int, int, int, int, int, int, int, void*, void*, cudaStream_t);
+int key_norm_scores(const void*, int64_t, int64_t, int64_t, int, int, int, int, int, int, void*, cudaStream_t);
 int append_rows(void*, void*, const void*, const void*, const int32_t*, const int32_t*, int, int, int, cudaStream_t);
 int flatten_regrow(void*, const void*, const int32_t*, const int32_t*, const int32_t*, int, int, int, int64_t, cudaStream_t);
 int update_flatten_view(void*, const void*, const void*, const int32_t*, const int32_t*, int, int, int, int64_t,
@@ -247,6 +248,15 @@ int kvc_gather_dense(const void* k, int64_t k_sb, int64_t k_sh, int64_t k_sl, co
   KVC_REQUIRE(elem_bytes == 2 || elem_bytes == 4, KVC_ERR_UNSUPPORTED, "elem_bytes %d", elem_bytes);
   return gather_dense(k, k_sb, k_sh, k_sl, v, v_sb, v_sh, v_sl, idx, B, Hq, Hkv, L, d, n_sel, w, elem_bytes, out_k,
                       out_v, (cudaStream_t)stream);
+}
+
+int kvc_key_norm_scores(const void* k, int64_t k_sb, int64_t k_sh, int64_t k_sl, int B, int Hq, int Hkv, int L, int d,
+                        int dtype, void* out_scores, void* stream) {
+  if (int rc = check_device()) return rc;
+  KVC_REQUIRE(k && out_scores, KVC_ERR_ARG, "null pointer argument");
+  KVC_REQUIRE(B > 0 && Hq > 0 && Hkv > 0 && Hq % Hkv == 0 && L > 0 && d > 0, KVC_ERR_ARG, "bad head geometry");
+  KVC_REQUIRE(dtype == KVC_BF16 || dtype == KVC_FP16, KVC_ERR_UNSUPPORTED, "dtype %d", dtype);
+  return key_norm_scores(k, k_sb, k_sh, k_sl, B, Hq, Hkv, L, d, dtype, out_scores, (cudaStream_t)stream);
 }
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }

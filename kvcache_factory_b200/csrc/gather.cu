@@ -165,6 +165,49 @@ int update_flatten_view(void* dst, const void* src, const void* state, const int
   return launch_status("flatten_append_kernel");
 }
 
+// ---- key L2 norms as selection scores (L2Norm policy, pyramidkv_utils.py:394-429) -------
+// out[b, hq, l] = -||K[b, hq / groups, l, :]||_2 in the model dtype (fp32 sum of squares, sqrt, one rounding, as
+// torch.norm on a 16-bit tensor), NEGATED so that the top-k select (largest first) yields the smallest norms in
+// ascending order -- the reference's argsort()[:cap].  One row per `lanes` = rowbytes / 16 threads.
+template <typename T>
+__global__ void __launch_bounds__(256)
+key_norm_kernel(const char* __restrict__ k, int64_t sb, int64_t sh, int64_t sl, int Hq, int groups, int L, int lanes,
+                uint16_t* __restrict__ out) {
+  const int rows_per_cta = 256 / lanes;
+  const int c = threadIdx.x % lanes, rg = threadIdx.x / lanes;
+  const int unit = blockIdx.y, b = unit / Hq, h = unit % Hq;
+  const int l = blockIdx.x * rows_per_cta + rg;
+  float ss = 0.f;
+  if (l < L && rg < rows_per_cta) {
+    const int4 q = ld_stream16(k + b * sb + (int64_t)(h / groups) * sh + (int64_t)l * sl + c * 16);
+    const uint32_t w4[4] = {(uint32_t)q.x, (uint32_t)q.y, (uint32_t)q.z, (uint32_t)q.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float a = T::to_float((uint16_t)(w4[i] & 0xffffu)), bb = T::to_float((uint16_t)(w4[i] >> 16));
+      ss = fmaf(a, a, ss);
+      ss = fmaf(bb, bb, ss);
+    }
+  }
+  for (int o = lanes >> 1; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if (c == 0 && l < L && rg < rows_per_cta) out[(int64_t)unit * L + l] = T::round1(-sqrtf(ss));
+}
+
+int key_norm_scores(const void* k, int64_t k_sb, int64_t k_sh, int64_t k_sl, int B, int Hq, int Hkv, int L, int d,
+                    int dtype, void* out, cudaStream_t stream) {
+  const int rowbytes = d * 2;
+  const int lanes = rowbytes / 16;
+  KVC_REQUIRE(rowbytes % 16 == 0 && lanes >= 1 && lanes <= 32 && (lanes & (lanes - 1)) == 0, KVC_ERR_UNSUPPORTED,
+              "head_dim %d: a row must be a power-of-two number (<= 32) of 16-byte chunks", d);
+  KVC_REQUIRE(aligned16(k) && ((k_sb | k_sh | k_sl) * 2) % 16 == 0, KVC_ERR_UNSUPPORTED, "key rows must be 16-byte aligned");
+  const int rows_per_cta = 256 / lanes;
+  dim3 grid((L + rows_per_cta - 1) / rows_per_cta, B * Hq);
+  if (dtype == KVC_BF16)
+    key_norm_kernel<Bf16><<<grid, 256, 0, stream>>>((const char*)k, k_sb * 2, k_sh * 2, k_sl * 2, Hq, Hq / Hkv, L, lanes, (uint16_t*)out);
+  else
+    key_norm_kernel<Fp16><<<grid, 256, 0, stream>>>((const char*)k, k_sb * 2, k_sh * 2, k_sl * 2, Hq, Hq / Hkv, L, lanes, (uint16_t*)out);
+  return launch_status("key_norm_kernel");
+}
+
 // ---- slack layout of the flattened cache: O(H*d) decode append ----------------------
 // Head h owns rows [cu_cap[h], cu_cap[h+1]) of the buffer and uses the first head_lens[h] of them.
 // append: the new row of head h goes to row cu_cap[h] + head_lens[h] of the K and of the V buffer (the caller bumps

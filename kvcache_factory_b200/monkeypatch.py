@@ -34,10 +34,10 @@ import torch
 
 from . import pyramidkv_utils as U
 
-DENSE_METHODS = ("pyramidkv", "snapkv", "h2o", "streamingllm")
+DENSE_METHODS = ("pyramidkv", "snapkv", "h2o", "streamingllm", "l2norm")
 FLAT_METHODS = ("adakv", "headkv")
 # methods of the reference that lie outside the hot path rebuilt here ("out of scope")
-UNSUPPORTED = ("cam", "l2norm", "minference", "think")
+UNSUPPORTED = ("cam", "minference", "think")
 
 _ORIGINAL: Dict[type, Callable] = {}
 
@@ -52,6 +52,8 @@ def _init_cluster(module, method: str) -> None:
         U.init_H2O(module)
     elif method == "streamingllm":
         U.init_StreamingLLM(module)
+    elif method == "l2norm":
+        U.init_l2norm(module)
     elif method == "adakv":
         U.init_adakv(module)
     elif method == "headkv":

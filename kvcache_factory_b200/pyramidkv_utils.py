@@ -393,6 +393,38 @@ class StreamingLLMKVCluster(_ScoredCluster):
                               self.max_capacity_prompt - self.window_size, scorer="none", pooling=None)
 
 
+class L2NormCluster:
+    """Reference ``L2NormCluster`` (``pyramidkv_utils.py:394-429``): keep the ``max_capacity_prompt`` keys of
+    smallest L2 norm per head, in ascending-norm order; no observation window, no queries (SURVEY.md section 8 f4:
+    the policy reuses the select and gather kernels, only the scores come from a different kernel)."""
+
+    keep_debug = False
+
+    def __init__(self, max_capacity_prompt: int = 256 + 64, layer_idx: int = 0, skip_layers: List[int] = []):
+        self.max_capacity_prompt = max_capacity_prompt
+        self.layer_idx = layer_idx
+        self.skip_layers = skip_layers
+
+    def reset(self, max_capacity_prompt: int = 256 + 64, layer_idx: int = 0, skip_layers: List[int] = []):
+        self.max_capacity_prompt = max_capacity_prompt
+        self.layer_idx = layer_idx
+        self.skip_layers = skip_layers
+
+    def update_kv(self, key_states, query_states, value_states, attention_mask, num_key_value_groups):
+        assert key_states.shape[-2] == query_states.shape[-2]        # :409
+        bsz, num_heads, q_len, head_dim = query_states.shape
+        _kv_heads(key_states, query_states, num_key_value_groups)
+        _trace(f"L2Norm max_capacity_prompt {self.max_capacity_prompt}")
+        if q_len < self.max_capacity_prompt or self.layer_idx in self.skip_layers:
+            return key_states, value_states                          # same objects (:414-417)
+        scores = N.key_norm_scores(key_states, num_heads)            # -||k||, model dtype (torch.norm keeps the dtype)
+        idx, _, _ = N.pool_topk(scores, 1, None, self.max_capacity_prompt)
+        out = N.gather_dense(key_states, value_states, idx, num_heads, self.max_capacity_prompt, 0)
+        if self.keep_debug:
+            self.debug = dict(scores=scores, indices=idx)
+        return out
+
+
 class AdaKVCluster:
     """Reference ``AdaKVCluster`` (``pyramidkv_utils.py:622-757``): head-adaptive budgets, flattened
     ``[sum_h len_h, d]`` cache plus the varlen metadata its decode path consumes
@@ -689,6 +721,14 @@ def init_StreamingLLM(self):
         window_size=self.config.window_size, max_capacity_prompt=self.config.max_capacity_prompt,
         kernel_size=self.config.kernel_size, pooling=self.config.pooling, merge=self.config.merge)
     _apply_async_knobs(self.kv_cluster, self.config)
+
+
+def init_l2norm(self):
+    """Reference ``init_l2norm`` (``pyramidkv_utils.py:954-968``)."""
+    if not hasattr(self, "kv_cluster"):
+        _defaults(self.config, max_capacity_prompt=4096, layer_idx=0, skip_layers=[0, 1])
+    self.kv_cluster = L2NormCluster(max_capacity_prompt=self.config.max_capacity_prompt, layer_idx=self.layer_idx,
+                                    skip_layers=self.config.skip_layers)
 
 
 def init_adakv(self):

@@ -208,6 +208,22 @@ def streamingllm_update_kv(K, Q, V, window_size=64, max_capacity_prompt=320):
     return Kc, Vc, idx, None
 
 
+def l2norm_update_kv(K, Q, V, max_capacity_prompt=320, layer_idx=0, skip_layers=()):
+    """``L2NormCluster.update_kv`` (``pyramidkv_utils.py:406-429``): the ``max_capacity_prompt`` keys of smallest L2
+    norm per head, ascending-norm order.  Returns (K', V', idx, norms); idx/norms None on the pass-through branches."""
+    assert K.shape[-2] == Q.shape[-2]
+    Kr, Vr = _expand(K, V, Q.shape[1])
+    if Q.shape[-2] < max_capacity_prompt or layer_idx in skip_layers:
+        return Kr, Vr, None, None
+    d = Kr.size(-1)
+    norms = torch.norm(Kr, p=2, dim=-1)                          # model dtype (:420)
+    order = norms.argsort(dim=-1)                                # ascending (:421)
+    gi = order.unsqueeze(-1).expand(-1, -1, -1, d)
+    Kc = Kr.gather(2, gi)[:, :, :max_capacity_prompt, :]
+    Vc = Vr.gather(2, gi)[:, :, :max_capacity_prompt, :]
+    return Kc, Vc, order[..., :max_capacity_prompt], norms
+
+
 # --------------------------------------------------------------------------------------------
 # a6  AdaKV
 # --------------------------------------------------------------------------------------------

@@ -68,6 +68,12 @@ CASES = {
     "headkv_bf16":        dict(method="headkv", B=1, Hq=8, Hkv=2, L=768, d=128, dtype="bf16", dist="peaked",
                                knobs=dict(window_size=32, kernel_size=7, pooling="maxpool", max_capacity_prompt=128,
                                           layer_idx=1, head_capacity=[[96] * 8, [10, 200, 96, 1, 736, 64, 300, 50]])),
+    "l2norm_bf16":        dict(method="l2norm", B=1, Hq=8, Hkv=2, L=640, d=128, dtype="bf16", dist="normal",
+                               knobs=dict(max_capacity_prompt=96, layer_idx=3, skip_layers=[0, 1])),
+    "l2norm_fp16":        dict(method="l2norm", B=2, Hq=4, Hkv=4, L=300, d=128, dtype="fp16", dist="peaked",
+                               knobs=dict(max_capacity_prompt=64, layer_idx=2, skip_layers=[])),
+    "l2norm_skip":        dict(method="l2norm", B=1, Hq=4, Hkv=2, L=200, d=128, dtype="bf16", dist="normal",
+                               knobs=dict(max_capacity_prompt=64, layer_idx=1, skip_layers=[0, 1])),
     "adakv_nocompress":   dict(method="adakv", B=1, Hq=4, Hkv=2, L=96, d=128, dtype="bf16", dist="normal",
                                knobs=dict(window_size=32, kernel_size=7, pooling="maxpool", max_capacity_prompt=128,
                                           floor=0.2, normalize=True)),
@@ -113,7 +119,7 @@ def run_case(ref, name: str, c: dict) -> dict:
     shape = Shape(c["B"], c["Hq"], c["Hkv"], c["L"], c["d"])
     dtype = DTYPES[c["dtype"]]
     kn = dict(c["knobs"])
-    w = kn["window_size"]
+    w = kn.get("window_size", 32)
     Q, K, V = make_qkv(shape, dtype, layer_idx=kn.get("layer_idx", 0), dist=c["dist"], window=w)
     Kr, Vr = ref.repeat_kv(K, shape.groups), ref.repeat_kv(V, shape.groups)
     out = {"inputs_digest": np.array(tensor_digest(Q, K, V))}
@@ -132,6 +138,10 @@ def run_case(ref, name: str, c: dict) -> dict:
         elif m == "streamingllm":
             cl = ref.StreamingLLMKVCluster(**kn)
             Kc, Vc = cl.update_kv(Kr, Q, Vr, None, shape.groups)
+        elif m == "l2norm":
+            cl = ref.L2NormCluster(**kn)
+            Kc, Vc = cl.update_kv(Kr, Q, Vr, None, shape.groups)
+            out["norms"] = bits(torch.norm(Kr, p=2, dim=-1))          # what update_kv sorts (:420)
         elif m in ("adakv", "headkv"):
             cl = ref.AdaKVCluster(**kn) if m == "adakv" else ref.HeadKVCluster(**kn)
             Kc, Vc = cl.update_kv(Kr, Q, Vr)

@@ -664,6 +664,41 @@ def test_scoring_implementations_agree_on_random_shapes():
 
 
 # ------------------------------------------------------------------------------------------------
+# f4: L2Norm (scores from the key norms; select + gather reused)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", golden_cases("l2norm"))
+def test_l2norm_matches_reference_vectors(name):
+    from kvcache_factory_b200 import L2NormCluster
+    c, z, (Q, K, V) = load_golden(name)
+    dtype = DTYPES[c["dtype"]]
+    g = c["Hq"] // c["Hkv"]
+    cl = L2NormCluster(**c["knobs"])
+    cl.keep_debug = True
+    Kd, Qd, Vd = K.to(dev()), Q.to(dev()), V.to(dev())
+    Kc, Vc = cl.update_kv(Kd, Qd, Vd, None, g)
+    torch.cuda.synchronize()
+    if name == "l2norm_skip":
+        assert Kc is Kd and Vc is Vd                     # same objects on the skip-layer branch (:416-417)
+        return
+    cap = c["knobs"]["max_capacity_prompt"]
+    assert tuple(Kc.shape) == tuple(z["K_out"].shape) and Kc.dtype == dtype
+    # norms: fp32 sum of squares + sqrt + one rounding; the accumulation order differs from ATen's -> <= 1 ulp
+    norms_ref = from_bits(z["norms"], dtype)
+    got = -cl.debug["scores"].cpu()
+    assert float(((got.float() - norms_ref.float()).abs() / norms_ref.float()).max()) <= 2 * ulp_of(dtype)
+    assert float((got == norms_ref).float().mean()) > 0.98
+    # the cap smallest norms (tie-aware, on the reference's own norms), ascending; gathered rows bit-exact
+    idx = cl.debug["indices"].cpu().long()
+    ok, msg = O.check_index_sets(-norms_ref, idx, cap, rtol=2 * ulp_of(dtype))
+    assert ok, msg
+    sel = norms_ref.float().gather(-1, idx)
+    assert bool((sel[..., 1:] >= sel[..., :-1] - 2 * ulp_of(dtype) * sel[..., 1:]).all()), "not in ascending-norm order"
+    Kr, Vr = O.repeat_kv(K, g), O.repeat_kv(V, g)
+    gi = idx.unsqueeze(-1).expand(-1, -1, -1, c["d"])
+    assert torch.equal(Kc.cpu(), Kr.gather(2, gi)) and torch.equal(Vc.cpu(), Vr.gather(2, gi))
+
+
+# ------------------------------------------------------------------------------------------------
 # f4: window scores from supplied statistics (log-sum-exp of the window rows), pass 2 only
 # ------------------------------------------------------------------------------------------------
 LSE_CASES = [(1, 8, 2, 777, 32), (2, 32, 8, 400, 8), (1, 16, 2, 1500, 32), (1, 32, 8, 4096, 32), (1, 32, 8, 2048, 16)]

@@ -44,6 +44,16 @@ def test_dense_policies_match_reference_vectors(name):
     assert np.array_equal(to_bits(Vc), z["V_out"])
 
 
+@pytest.mark.parametrize("name", golden_cases("l2norm"))
+def test_l2norm_matches_reference_vectors(name):
+    c, z, (Q, K, V) = load_golden(name)
+    Kc, Vc, idx, norms = O.l2norm_update_kv(K, Q, V, **c["knobs"])
+    assert tuple(Kc.shape) == tuple(z["K_out"].shape)
+    assert np.array_equal(to_bits(Kc), z["K_out"]) and np.array_equal(to_bits(Vc), z["V_out"])
+    if norms is not None:
+        assert np.array_equal(to_bits(norms), z["norms"])
+
+
 @pytest.mark.parametrize("name", golden_cases("adakv"))
 def test_adakv_matches_reference_vectors(name):
     c, z, (Q, K, V) = load_golden(name)
