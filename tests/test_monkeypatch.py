@@ -49,7 +49,7 @@ def test_method_strings_and_restore():
     import transformers.models.llama.modeling_llama as L
     import transformers.models.mistral.modeling_mistral as M
     orig_l, orig_m = L.LlamaAttention.forward, M.MistralAttention.forward
-    for m in ("pyramidkv", "snapkv", "h2o", "streamingllm", "adakv", "headkv"):
+    for m in ("pyramidkv", "snapkv", "h2o", "streamingllm", "l2norm", "adakv", "headkv"):
         kvc.replace_llama(m)
         assert L.LlamaAttention.forward is not orig_l and m in L.LlamaAttention.forward.__name__
         kvc.replace_mistral(m)
@@ -59,7 +59,7 @@ def test_method_strings_and_restore():
     assert L.LlamaAttention.forward is orig_l and M.MistralAttention.forward is orig_m
     kvc.replace_llama("fullkv")
     assert L.LlamaAttention.forward is orig_l
-    for m in ("cam", "l2norm", "think", "minference"):
+    for m in ("cam", "think", "minference"):
         with pytest.raises(NotImplementedError):
             kvc.replace_llama(m)
     with pytest.raises(ValueError):
