@@ -562,17 +562,15 @@ window_score_fused_kernel(const __grid_constant__ CUtensorMap tmap_k, const Para
 }
 
 // =====================================================================================================
-// Half-footprint variant: the same two passes in a CTA HALF the size (8 epilogue warps, 2 accumulator
-// buffers = 256 TMEM columns, 2 K stages, ~100 KB of shared memory, <= 96 registers) so that TWO CTAs --
+// Half-footprint variant: the same two passes in a CTA HALF the size (2 accumulator buffers = 256 TMEM
+// columns, 2 K stages, ~100 KB of shared memory, half the register file) so that TWO CTAs --
 // of two different launches -- share an SM.  A single launch leaves ~9 us of every ~34 us idle on every SM
 // (prologue, grid-barrier skew, statistics fold, tail); with the scoring launches of consecutive layers on
-// two streams those gaps are filled by the other layer's CTA.  Warpgroup g owns columns [64g, 64g+64) of
-// every tile (two 32-column chunks).  Two launches are in flight at once, so the grid barrier uses one
+// two streams those gaps are filled by the other layer's CTA.  Warpgroup g owns columns [g*128/NWG, (g+1)*128/NWG)
+// of every tile.  Two launches are in flight at once, so the grid barrier uses one
 // pair of library-owned, self-resetting words per STREAM.  RB == 1 only.
-constexpr int kHEpiWarps = 8;
-constexpr int kHNumWG = 2;
-constexpr int kHEpiThreads = kHEpiWarps * 32;
-constexpr int kHThreads = 32 * (2 + kHEpiWarps);
+// NWG warpgroups share every tile: 2 (two 32-column chunks each, <= 96 registers) or 4 (one chunk each, <= 56
+// registers: twice the warps per SM sub-partition to cover each other's tcgen05.ld and barrier latencies).
 constexpr int kHNumBuf = 2;
 
 struct HalfSmem {
@@ -583,20 +581,24 @@ struct HalfSmem {
   static constexpr int kNumBars = 2 * kStages + 2 * kHNumBuf + 1;
   static constexpr int kTmemPtrOff = kBarOff + kNumBars * 8;
   static constexpr int kCrowOff = (kTmemPtrOff + 4 + 15) & ~15;   // float[128]
-  static constexpr int kXstatOff = kCrowOff + 128 * 4;            // float2[2][128]
-  static constexpr int kTotal = kXstatOff + 2 * 128 * 8;
+  static constexpr int kXstatOff = kCrowOff + 128 * 4;            // float2[NWG <= 4][128]
+  static constexpr int kTotal = kXstatOff + 4 * 128 * 8;
   static constexpr int kAlloc = kTotal + 1024;
 };
 
 constexpr int kHSlots = 16;
 __device__ unsigned g_hbar_count[kHSlots], g_hbar_gen[kHSlots];   // zero at module load, self-resetting
 
-__device__ __forceinline__ void hepi_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kHEpiThreads) : "memory"); }
+template <int kN>
+__device__ __forceinline__ void hepi_sync_n() { asm volatile("bar.sync 1, %0;" ::"n"(kN) : "memory"); }
 
-template <typename T, int W>
-__global__ void __launch_bounds__(kHThreads, 2)
+template <typename T, int W, int NWG>
+__global__ void __launch_bounds__(64 + 128 * NWG, 2)
 window_score_half_kernel(const __grid_constant__ CUtensorMap tmap_k, const Params p, int slot) {
   using SM = HalfSmem;
+  constexpr int kHEpiWarps = 4 * NWG, kHEpiThreads = 128 * NWG;
+  constexpr int kCols = 128 / NWG, kChunks = kCols / 32;   // columns / 32-column chunks of a tile per warpgroup
+  auto hepi_sync = [] { hepi_sync_n<kHEpiThreads>(); };
   constexpr int S = SM::kStages;
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -708,7 +710,7 @@ window_score_half_kernel(const __grid_constant__ CUtensorMap tmap_k, const Param
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     mbar_arrive(qbar);
 
-    const uint32_t tcol = tmem_base + ((uint32_t)(quad * 32) << 16) + wg * 64;
+    const uint32_t tcol = tmem_base + ((uint32_t)(quad * 32) << 16) + wg * kCols;
     const bool dead_rows = __all_sync(0xffffffffu, r_loc / W >= p.groups);
     // ---------------- pass 1 ----------------
     float m_run = -1e30f;
@@ -716,7 +718,7 @@ window_score_half_kernel(const __grid_constant__ CUtensorMap tmap_k, const Param
     int j = 0;
     for (; j < n1; ++j) {
       const int buf = j % kHNumBuf;
-      const int key0 = tile_of(j) * kTile + wg * 64;
+      const int key0 = tile_of(j) * kTile + wg * kCols;
       mbar_wait(tfull(buf), (j / kHNumBuf) & 1);
       tc_fence_after();
       if (dead_rows) {
@@ -724,20 +726,20 @@ window_score_half_kernel(const __grid_constant__ CUtensorMap tmap_k, const Param
         if (lane == 0) mbar_arrive(tempty(buf));
         continue;
       }
-      uint32_t va[32], vb[32];
+      uint32_t va[32], vb[kChunks == 2 ? 32 : 1];
       tmem_ld32(tcol + buf * 128, va);
-      tmem_ld32(tcol + buf * 128 + 32, vb);
+      if constexpr (kChunks == 2) tmem_ld32(tcol + buf * 128 + 32, vb);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty(buf));
-      if (key0 + 64 > nscore) {
+      if (key0 + kCols > nscore) {
         const int last_key = min(p.L - 1, r_loc / W < p.groups ? nscore + r_loc % W : p.L - 1);
         p1_chunk<T, true>(va, scale, m_run, zacc, key0, last_key);
-        p1_chunk<T, true>(vb, scale, m_run, zacc, key0 + 32, last_key);
+        if constexpr (kChunks == 2) p1_chunk<T, true>(vb, scale, m_run, zacc, key0 + 32, last_key);
       } else {
         p1_chunk<T, false>(va, scale, m_run, zacc, 0, 0);
-        p1_chunk<T, false>(vb, scale, m_run, zacc, 0, 0);
+        if constexpr (kChunks == 2) p1_chunk<T, false>(vb, scale, m_run, zacc, 0, 0);
       }
     }
     // ---------------- publish, grid barrier, fold ----------------
@@ -747,9 +749,12 @@ window_score_half_kernel(const __grid_constant__ CUtensorMap tmap_k, const Param
     }
     hepi_sync();
     if (et < 128) {
-      const float2 a = xstat[et], c = xstat[128 + et];
-      const float mn = fmaxf(a.x, c.x);
-      const float z = a.y * fast_exp2((a.x - mn) * kLog2e) + c.y * fast_exp2((c.x - mn) * kLog2e);
+      float mn = xstat[et].x;
+#pragma unroll
+      for (int g = 1; g < NWG; ++g) mn = fmaxf(mn, xstat[g * 128 + et].x);
+      float z = 0.f;
+#pragma unroll
+      for (int g = 0; g < NWG; ++g) { const float2 a = xstat[g * 128 + et]; z += a.y * fast_exp2((a.x - mn) * kLog2e); }
       p.stats[((int64_t)unit * p.nchunks + chunk) * 128 + et] = make_float2(mn, z);
     }
     __threadfence();
@@ -804,9 +809,12 @@ window_score_half_kernel(const __grid_constant__ CUtensorMap tmap_k, const Param
       xstat[q * 128 + r] = make_float2(M, Z);
       hepi_sync();
       if (et < 128) {
-        const float2 a = xstat[et], c = xstat[128 + et];
-        const float mx = fmaxf(a.x, c.x);
-        const float z = a.y * fast_exp2((a.x - mx) * kLog2e) + c.y * fast_exp2((c.x - mx) * kLog2e);
+        float mx = xstat[et].x;
+#pragma unroll
+        for (int g = 1; g < kParts; ++g) mx = fmaxf(mx, xstat[g * 128 + et].x);
+        float z = 0.f;
+#pragma unroll
+        for (int g = 0; g < kParts; ++g) { const float2 a = xstat[g * 128 + et]; z += a.y * fast_exp2((a.x - mx) * kLog2e); }
         crow[et] = (et / W < p.groups) ? (-mx * kLog2e - log2f(z)) : -INFINITY;
       }
     }
@@ -818,26 +826,27 @@ window_score_half_kernel(const __grid_constant__ CUtensorMap tmap_k, const Param
       const int key = tile_of(j) * kTile + r_loc;
       mbar_wait(tfull(buf), (j / kHNumBuf) & 1);
       tc_fence_after();
-      if ((wg * 64) / W >= p.groups) {  // both chunks of this warpgroup lie beyond the last head
+      if ((wg * kCols) / W >= p.groups) {  // all chunks of this warpgroup lie beyond the last head
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty(buf));
         continue;
       }
-      uint32_t va[32], vb[32];
+      uint32_t va[32], vb[kChunks == 2 ? 32 : 1];
       tmem_ld32(tcol + buf * 128, va);
-      tmem_ld32(tcol + buf * 128 + 32, vb);
+      if constexpr (kChunks == 2) tmem_ld32(tcol + buf * 128 + 32, vb);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty(buf));
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const int col0 = wg * 64 + c * 32;
+      for (int c = 0; c < kChunks; ++c) {
+        const int col0 = wg * kCols + c * 32;
         if (col0 / W >= p.groups) continue;
         float2 acc[kHeadsPerChunk];
 #pragma unroll
         for (int h = 0; h < kHeadsPerChunk; ++h) acc[h] = make_float2(0.f, 0.f);
-        p2_chunk<T, W>(c == 0 ? va : vb, scale, crow + col0, acc);
+        if constexpr (kChunks == 2) p2_chunk<T, W>(c == 0 ? va : vb, scale, crow + col0, acc);
+        else p2_chunk<T, W>(va, scale, crow + col0, acc);
         if (key < nscore) {
 #pragma unroll
           for (int h = 0; h < kHeadsPerChunk; ++h) {
@@ -878,16 +887,16 @@ static int half_slot(cudaStream_t stream) {
   return n[dev]++;
 }
 
-template <typename T, int W>
+template <typename T, int W, int NWG>
 static int launch_half(const CUtensorMap& tmap, const Params& sp, int units, cudaStream_t stream) {
-  auto kern = window_score_half_kernel<T, W>;
+  auto kern = window_score_half_kernel<T, W, NWG>;
   const int smem = HalfSmem::kAlloc;
   KVC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int slot = half_slot(stream);
   KVC_REQUIRE(slot >= 0, KVC_ERR_UNSUPPORTED, "half-footprint tcgen05 scoring kernel: more than %d distinct streams on this device", kHSlots);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(sp.nchunks, units);
-  cfg.blockDim = dim3(kHThreads);
+  cfg.blockDim = dim3(64 + 128 * NWG);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   // no programmatic dependent launch here: with two launches in flight a pre-launched successor of the same
@@ -898,10 +907,21 @@ static int launch_half(const CUtensorMap& tmap, const Params& sp, int units, cud
 
 template <typename T>
 static int dispatch_half(const CUtensorMap& tmap, const Params& sp, int units, cudaStream_t stream) {
+  // four warpgroups (56 registers, 8 epilogue warps per SM sub-partition with two CTAs on the SM) measured 29.0 vs
+  // 29.9 us per launch with two launches in flight, 1.431 vs 1.452 ms per cfg-2 step; KVC_HALF_WG=2 selects the
+  // two-warpgroup build
+  static const bool four = [] { const char* e = getenv("KVC_HALF_WG"); return !(e && atoi(e) == 2); }();
+  if (four) {
+    switch (sp.w) {
+      case 8: return launch_half<T, 8, 4>(tmap, sp, units, stream);
+      case 16: return launch_half<T, 16, 4>(tmap, sp, units, stream);
+      default: return launch_half<T, 32, 4>(tmap, sp, units, stream);
+    }
+  }
   switch (sp.w) {
-    case 8: return launch_half<T, 8>(tmap, sp, units, stream);
-    case 16: return launch_half<T, 16>(tmap, sp, units, stream);
-    default: return launch_half<T, 32>(tmap, sp, units, stream);
+    case 8: return launch_half<T, 8, 2>(tmap, sp, units, stream);
+    case 16: return launch_half<T, 16, 2>(tmap, sp, units, stream);
+    default: return launch_half<T, 32, 2>(tmap, sp, units, stream);
   }
 }
 
