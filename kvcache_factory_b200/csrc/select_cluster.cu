@@ -2,14 +2,16 @@
 // (B*Hq = 32 at batch 1) still occupies most of the chip.
 //
 // CTA c of the C-CTA cluster owns the contiguous slice [c*SL, (c+1)*SL) of the row (SL = 1024*E).
-//   1. stage slice + pooling halo in shared memory (coalesced), pool, keep 16-bit keys in registers
-//   2. exact k-th largest key in at most two counting rounds over a DATA-ADAPTIVE binning: the row's
-//      key range [kmin, kmax] is split into <= 256 bins of 2^sh keys, the threshold bin is located,
-//      then (if sh > 0) its 2^sh <= 256 keys are resolved.  Counting uses warp-private shared-memory
-//      histograms (plain atomics: the adaptive bins spread the keys, so same-address conflicts are
-//      rare); per-CTA histograms are exchanged through distributed shared memory.
-//   3. winners are compacted in index order (block scan + per-CTA bases exchanged through DSMEM) and
-//      written straight into CTA 0's shared memory with st.shared::cluster
+//   1. load the slice + pooling halo into registers (16-byte vectors), pool, keep 16-bit keys in registers
+//   2. k-th largest key in at most two counting rounds over a DATA-ADAPTIVE binning: the row's key range
+//      [kmin, kmax] is split into <= 256 bins of 2^sh keys and the threshold bin is located.  If that bin's
+//      keys fit the sort buffers next to the winners they simply go along (step 4 orders them and the first k
+//      sorted entries are the answer); otherwise a second round resolves its 2^sh <= 256 keys.  Counting uses
+//      warp-private shared-memory histograms (plain atomics: the adaptive bins spread the keys, so
+//      same-address conflicts are rare); per-CTA histograms are read through distributed shared memory.
+//   3. winners are compacted in index order (block scan; the bases of a CTA follow from the lower-ranked
+//      CTAs' histograms, no further exchange) and written straight into CTA 0's shared memory with
+//      st.shared::cluster; the other CTAs exit
 //   4. CTA 0 orders them with a stable 2-pass LSD radix sort (O(k), ranks from match.any) and emits
 //      indices by descending value, ascending position among equal values (torch.topk sorted=True,
 //      deterministic on ties)
@@ -23,8 +25,12 @@ namespace cl {
 
 #ifdef KVC_TRACE
 __device__ long long g_sel_trace[16];
+__device__ long long g_sel_gt[8];
 #define SEL_STAMP(slot) do { if (blockIdx.y == 0 && blockIdx.x == 0 && threadIdx.x == 0) g_sel_trace[slot] = clock64(); } while (0)
+__device__ long long g_sel_tail[16];
+#define TAIL_STAMP(slot) do { if (blockIdx.y == 0 && blockIdx.x == 3 && (threadIdx.x == blockDim.x - 1 || threadIdx.x == 0)) { asm volatile("" ::: "memory"); g_sel_tail[slot + (threadIdx.x == 0 ? 8 : 0)] = clock64(); } } while (0)
 #else
+#define TAIL_STAMP(slot) do { } while (0)
 #define SEL_STAMP(slot) do { } while (0)
 #endif
 
@@ -45,6 +51,7 @@ __device__ __forceinline__ uint32_t map_to_rank(const void* local, uint32_t rank
 __device__ __forceinline__ uint32_t ld_cluster_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
 __device__ __forceinline__ float ld_cluster_f32(uint32_t a) { float v; asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory"); return v; }
 __device__ __forceinline__ void st_cluster_u32(uint32_t a, uint32_t v) { asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void st_cluster_f32(uint32_t a, float v) { asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
 __device__ __forceinline__ void st_cluster_u16(uint32_t a, uint16_t v) { asm volatile("st.shared::cluster.u16 [%0], %1;" ::"r"(a), "h"(v) : "memory"); }
 
 template <int kWarps>
@@ -55,9 +62,11 @@ struct SharedT {
   int warp_tmp2[32];
   float fsum[32];
   int mm[2];                // min / max key of this CTA's slice
-  int totals[2];            // selected-above / equal-to-threshold counts of this CTA
   float psum[2];            // partial sums (selected, all) of this CTA
-  int sel_digit, sel_above; // result of the per-round threshold search
+  float cpsum[16][2];       // CTA 0 only: every CTA's partial sums, written remotely before the last cluster barrier
+  int sel_digit, sel_above, sel_cnt; // result of the per-round threshold search (+ population of the threshold bin)
+  int sel_labove, sel_lcnt;          // the same two counts restricted to the CTAs of lower rank (= lower positions)
+  unsigned long long warp_tmp64[32];
 };
 
 // Exclusive block scan of one int per thread (kWarps warps, <= 32).
@@ -85,6 +94,30 @@ __device__ __forceinline__ int block_scan_excl(int v, int* warp_tmp, int& total)
   return base + inc - v;
 }
 
+// The same for a pair of counts packed into 64 bits (low word, high word; neither overflows 32 bits).
+template <int kWarps>
+__device__ __forceinline__ unsigned long long block_scan_excl64(unsigned long long v, unsigned long long* warp_tmp) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  unsigned long long inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  __syncthreads();
+  if (lane == 31) warp_tmp[wid] = inc;
+  __syncthreads();
+  const unsigned long long mine = lane < kWarps ? warp_tmp[lane] : 0ull;
+  unsigned long long pre = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long t = __shfl_up_sync(0xffffffffu, pre, o);
+    if (lane >= o) pre += t;
+  }
+  const unsigned long long base = __shfl_sync(0xffffffffu, pre - mine, wid);
+  return base + inc - v;
+}
+
 template <int kWarps>
 __device__ __forceinline__ float block_sum_f(float v, float* tmp) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -97,6 +130,21 @@ __device__ __forceinline__ float block_sum_f(float v, float* tmp) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
   return r;
+}
+
+// s / d, correctly rounded, from a precomputed reciprocal: quotient estimate, exact remainder, one correction
+// (Markstein).  Tiny numerators are scaled by 2^64 first so that the remainder cannot underflow (the scaling is
+// exact; only a subnormal quotient is rounded a second time).  No `/` anywhere: a zero numerator -- underflowed
+// probabilities, the padded tail of a row -- sends the compiler's division down its special-case subroutine, and the
+// one warp holding the tail then held the whole cluster at its first barrier for 2 us (scripts/trace_sel.py,
+// n = 32736 against 32768: 25.3k against 21.3k cycles per row).
+__device__ __forceinline__ float div_exact(float s, float d, float rcp) {
+  const bool tiny = fabsf(s) < 1e-30f;
+  const float up = tiny ? 0x1p64f : 1.0f, down = tiny ? 0x1p-64f : 1.0f;
+  const float a = s * up;
+  const float q = a * rcp;
+  const float r = fmaf(-q, d, a);
+  return fmaf(r, rcp, q) * down;
 }
 
 // Stable rank: add one occurrence of `digit` per lane to this warp's counters and return the
@@ -113,19 +161,32 @@ __device__ __forceinline__ int warp_rank_digit(int* wh, int digit, int lane) {
 
 // Sum the cluster's per-CTA histograms of `round` and find the bin at which the descending running
 // count reaches krem.  Every CTA computes the same answer.  Threads 0..255 <-> bins 255..0.
+// The per-CTA histograms also tell every CTA how many keys above / inside the threshold bin lie in the CTAs of
+// lower rank (l_above, l_in): the bases of the ordered compaction, without another exchange.
 template <int kWarps>
-__device__ __forceinline__ void cluster_threshold(SharedT<kWarps>& sh, int round, int krem, uint32_t csize, int& digit, int& above) {
+__device__ __forceinline__ void cluster_threshold(SharedT<kWarps>& sh, int round, int krem, uint32_t csize, uint32_t crank,
+                                                  int& digit, int& above, int& in_bin, int& l_above, int& l_in) {
   const int tid = threadIdx.x;
   const int d = 255 - tid;
-  int cnt = 0;
+  unsigned cnt = 0, low = 0;
   if (tid < 256)
-    for (uint32_t c = 0; c < csize; ++c) cnt += (int)ld_cluster_u32(map_to_rank(&sh.hist[round][d], c));
-  int total;
-  const int ex = block_scan_excl<kWarps>(cnt, sh.warp_tmp, total);
-  if (tid < 256 && ex < krem && ex + cnt >= krem) { sh.sel_digit = d; sh.sel_above = ex; }
+    for (uint32_t c = 0; c < csize; ++c) {
+      const unsigned v = ld_cluster_u32(map_to_rank(&sh.hist[round][d], c));
+      cnt += v;
+      if (c < crank) low += v;
+    }
+  const unsigned long long ex64 = block_scan_excl64<kWarps>((unsigned long long)cnt | ((unsigned long long)low << 32), sh.warp_tmp64);
+  const int ex = (int)(unsigned)ex64;
+  if (tid < 256 && ex < krem && ex + (int)cnt >= krem) {
+    sh.sel_digit = d; sh.sel_above = ex; sh.sel_cnt = (int)cnt;
+    sh.sel_labove = (int)(ex64 >> 32); sh.sel_lcnt = (int)low;
+  }
   __syncthreads();
   digit = sh.sel_digit;
   above = sh.sel_above;
+  in_bin = sh.sel_cnt;
+  l_above = sh.sel_labove;
+  l_in = sh.sel_lcnt;
 }
 
 // One counting round: bins of the participating keys -> warp-private atomics -> CTA histogram.
@@ -160,7 +221,6 @@ topk_cluster_kernel(const uint16_t* __restrict__ scores, int n, int kernel_size,
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Shared& sh = *reinterpret_cast<Shared*>(smem_raw);
   unsigned char* dyn = smem_raw + ((sizeof(Shared) + 15) & ~15);
-  uint16_t* stage = reinterpret_cast<uint16_t*>(dyn);   // phase 1: chunk stride E+2 u16 (odd word stride)
   // phase 3-4 (CTA 0 only, written remotely): keys/indices ping-pong
   uint16_t* skey[2] = {reinterpret_cast<uint16_t*>(dyn), reinterpret_cast<uint16_t*>(dyn) + kMaxKT};
   uint32_t* sidx[2] = {reinterpret_cast<uint32_t*>(dyn + 4 * kMaxKT), reinterpret_cast<uint32_t*>(dyn + 4 * kMaxKT) + kMaxKT};
@@ -173,8 +233,15 @@ topk_cluster_kernel(const uint16_t* __restrict__ scores, int n, int kernel_size,
   k = min(max(k, 0), n);
   const int radius = POOL == KVC_POOL_NONE ? 0 : kernel_size / 2;
   const int s0 = (int)crank * SL;
+  const float ksf = (float)kernel_size, krcp = 1.0f / ksf;
 
   SEL_STAMP(0);
+#ifdef KVC_TRACE
+  if (blockIdx.y == 0 && threadIdx.x == 0 && blockIdx.x < 4) {
+    unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+    g_sel_gt[blockIdx.x] = (long long)g;
+  }
+#endif
   // ---- 1. load this thread's E scores (+ pooling halo) straight into registers, pool -------------
   // Own elements: 8-element (16-byte) vector loads when the row allows it -- a warp then reads one
   // contiguous span; the 2*kHalo halo elements are the neighbours' own elements (L1 hits).
@@ -200,6 +267,7 @@ topk_cluster_kernel(const uint16_t* __restrict__ scores, int n, int kernel_size,
 #pragma unroll
       for (int i = 0; i < E; ++i) raw[kHalo + i] = j0 + i < n ? __ldg(srow + j0 + i) : (uint16_t)0;
     }
+    TAIL_STAMP(0);
     if (POOL != KVC_POOL_NONE) {
 #pragma unroll
       for (int i = 0; i < kHalo; ++i) {
@@ -208,20 +276,16 @@ topk_cluster_kernel(const uint16_t* __restrict__ scores, int n, int kernel_size,
         raw[kHalo + E + i] = jr < n ? __ldg(srow + jr) : (uint16_t)0;
       }
     }
-    float f[E + 2 * kHalo];
-    uint32_t kk[E + 2 * kHalo];
+    // slots outside the row hold zero bits (= +0.0): the zero padding of avg_pool1d needs no test; max pooling pads
+    // with the lowest key instead
+    TAIL_STAMP(1);
+    if (POOL == KVC_POOL_AVG) {
+      float f[E + 2 * kHalo];
 #pragma unroll
-    for (int i = 0; i < E + 2 * kHalo; ++i) {
-      const int j = j0 - kHalo + i;
-      const bool in = j >= 0 && j < n;
-      if (POOL == KVC_POOL_AVG) f[i] = in ? T::to_float(raw[i]) : 0.f;
-      else kk[i] = in ? float16_bits_to_key(raw[i]) : 0u;
-    }
+      for (int i = 0; i < E + 2 * kHalo; ++i) f[i] = T::to_float(raw[i]);
 #pragma unroll
-    for (int i = 0; i < E; ++i) {
-      uint32_t bits;
-      if (POOL == KVC_POOL_AVG) {
-        float s = 0.f;  // ascending position, zero padding, divisor = kernel_size (ATen avg_pool)
+      for (int i = 0; i < E; ++i) {
+        float s = 0.f;  // ascending position, divisor = kernel_size (ATen avg_pool)
         if (radius >= 3) s += f[i];
         if (radius >= 2) s += f[i + 1];
         if (radius >= 1) s += f[i + 2];
@@ -229,9 +293,17 @@ topk_cluster_kernel(const uint16_t* __restrict__ scores, int n, int kernel_size,
         if (radius >= 1) s += f[i + 4];
         if (radius >= 2) s += f[i + 5];
         if (radius >= 3) s += f[i + 6];
-        bits = T::round1(s / (float)kernel_size);
-        keys[i] = float16_bits_to_key(bits);
-      } else {
+        keys[i] = float16_bits_to_key(T::round1(div_exact(s, ksf, krcp)));
+      }
+    } else {
+      uint32_t kk[E + 2 * kHalo];
+#pragma unroll
+      for (int i = 0; i < E + 2 * kHalo; ++i) {
+        const int j = j0 - kHalo + i;
+        kk[i] = (j >= 0 && j < n) ? float16_bits_to_key(raw[i]) : 0u;
+      }
+#pragma unroll
+      for (int i = 0; i < E; ++i) {
         uint32_t best = kk[i + 3];
         if (POOL == KVC_POOL_MAX) {
           if (radius >= 1) best = max(best, max(kk[i + 2], kk[i + 4]));
@@ -239,16 +311,26 @@ topk_cluster_kernel(const uint16_t* __restrict__ scores, int n, int kernel_size,
           if (radius >= 3) best = max(best, max(kk[i], kk[i + 6]));
         }
         keys[i] = best;
-        bits = key_to_float16_bits(best);
-      }
-      if (j0 + i < n) {
-        part_all += T::to_float((uint16_t)bits);
-        if (out_pooled) out_pooled[(int64_t)row * n + j0 + i] = (uint16_t)bits;
-      } else {
-        keys[i] = 0u;
       }
     }
+    TAIL_STAMP(2);
+    if (j0 + E > n) {   // ragged end of the row (warp-uniform except in one warp)
+#pragma unroll
+      for (int i = 0; i < E; ++i)
+        if (j0 + i >= n) keys[i] = 0u;
+    }
+    if (out_pooled) {
+#pragma unroll
+      for (int i = 0; i < E; ++i)
+        if (j0 + i < n) out_pooled[(int64_t)row * n + j0 + i] = (uint16_t)key_to_float16_bits(keys[i]);
+    }
+    if (out_sums) {
+#pragma unroll
+      for (int i = 0; i < E; ++i)
+        if (j0 + i < n) part_all += T::to_float((uint16_t)key_to_float16_bits(keys[i]));
+    }
   }
+    TAIL_STAMP(3);
   SEL_STAMP(1);
   const int nvalid = max(0, min(E, n - j0));
   const float sum_all_cta = out_sums ? block_sum_f<kWarps>(part_all, sh.fsum) : 0.f;
@@ -273,6 +355,7 @@ topk_cluster_kernel(const uint16_t* __restrict__ scores, int n, int kernel_size,
 #pragma unroll
   for (int i = 0; i < E; ++i)
     if (i < nvalid) { kmin = min(kmin, (int)keys[i]); kmax = max(kmax, (int)keys[i]); }
+    TAIL_STAMP(4);
   kmin = __reduce_min_sync(0xffffffffu, kmin);
   kmax = __reduce_max_sync(0xffffffffu, kmax);
   if (lane == 0) { sh.warp_tmp[wid] = kmin; sh.warp_tmp2[wid] = kmax; }
@@ -282,7 +365,15 @@ topk_cluster_kernel(const uint16_t* __restrict__ scores, int n, int kernel_size,
     const int b2 = __reduce_max_sync(0xffffffffu, lane < kWarps ? sh.warp_tmp2[lane] : 0);
     if (lane == 0) { sh.mm[0] = a; sh.mm[1] = b2; }
   }
+  SEL_STAMP(9);
+#ifdef KVC_TRACE
+  if (blockIdx.y == 0 && threadIdx.x == 0 && blockIdx.x < 4) {
+    unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+    g_sel_gt[4 + blockIdx.x] = (long long)g;
+  }
+#endif
   cluster_sync();
+  SEL_STAMP(10);
   kmin = 0xffff; kmax = 0;
   for (uint32_t c = 0; c < csize; ++c) {
     kmin = min(kmin, (int)ld_cluster_u32(map_to_rank(&sh.mm[0], c)));
@@ -293,30 +384,46 @@ topk_cluster_kernel(const uint16_t* __restrict__ scores, int n, int kernel_size,
 
   SEL_STAMP(3);
   // ---- 2b. counting rounds -----------------------------------------------------------------------------
-  int krem = k, thr_key;
+  // After the rounds: keys >= thr_hi are winners (count_gt of them), keys in [thr_key, thr_hi) are CANDIDATES of
+  // which the first need_eq in (descending key, ascending position) order complete the k.  An exact threshold has
+  // thr_hi = thr_key + 1.  When the whole threshold bin of round one fits the sort buffers next to the winners, round
+  // two is skipped: the bin's keys all go to the sort, which orders them anyway, and the first k sorted entries are
+  // the answer (one counting round, one cluster barrier and one threshold search less on the latency chain).
+  int krem = k, thr_key, thr_hi, nsort = k;
+  int gbase, ebase;   // winners / candidates held by the CTAs of lower rank
   {
     int bin[E];
 #pragma unroll
     for (int i = 0; i < E; ++i) bin[i] = i < nvalid ? ((int)keys[i] - kmin) >> sh1 : -1;
     count_round<E, kWarps>(sh, 0, bin, lane, wid);
+    SEL_STAMP(11);
     cluster_sync();  // every CTA's hist[0] is complete and visible
-    int b1, above;
-    cluster_threshold<kWarps>(sh, 0, krem, csize, b1, above);
+    SEL_STAMP(12);
+    int b1, above, in_bin;
+    cluster_threshold<kWarps>(sh, 0, krem, csize, crank, b1, above, in_bin, gbase, ebase);
     krem -= above;
     thr_key = kmin + (b1 << sh1);
+    thr_hi = thr_key + (1 << sh1);
     if (sh1 > 0) {
+      if (out_idx != nullptr && out_sums == nullptr && above + in_bin <= kMaxKT) {
+        krem = in_bin;              // take the whole bin along
+        nsort = above + in_bin;
+      } else {
 #pragma unroll
-      for (int i = 0; i < E; ++i) bin[i] = (bin[i] == b1) ? ((int)keys[i] - thr_key) : -1;
-      count_round<E, kWarps>(sh, 1, bin, lane, wid);
-      cluster_sync();
-      int b2v, above2;
-      cluster_threshold<kWarps>(sh, 1, krem, csize, b2v, above2);
-      krem -= above2;
-      thr_key += b2v;
+        for (int i = 0; i < E; ++i) bin[i] = (bin[i] == b1) ? ((int)keys[i] - thr_key) : -1;
+        count_round<E, kWarps>(sh, 1, bin, lane, wid);
+        cluster_sync();
+        int b2v, above2, in2, l_above2;
+        cluster_threshold<kWarps>(sh, 1, krem, csize, crank, b2v, above2, in2, l_above2, ebase);
+        gbase += l_above2;
+        krem -= above2;
+        thr_key += b2v;
+        thr_hi = thr_key + 1;
+      }
     }
   }
   SEL_STAMP(4);
-  const int need_eq = krem, count_gt = k - krem;
+  const int need_eq = krem, count_gt = nsort - krem;
 
   if (out_idx == nullptr) {
     // Sums only (AdaKV's ratio normalisation, pyramidkv_utils.py:706-711): the sum of the k largest
@@ -348,55 +455,61 @@ topk_cluster_kernel(const uint16_t* __restrict__ scores, int n, int kernel_size,
   int gt = 0, eq = 0;
 #pragma unroll
   for (int i = 0; i < E; ++i) {
-    gt += (i < nvalid && (int)keys[i] > thr_key);
-    eq += (i < nvalid && (int)keys[i] == thr_key);
+    gt += (i < nvalid && (int)keys[i] >= thr_hi);
+    eq += (i < nvalid && (int)keys[i] >= thr_key && (int)keys[i] < thr_hi);
   }
   int total;
   const int ex = block_scan_excl<kWarps>(gt | (eq << 16), sh.warp_tmp, total);
-  if (tid == 0) { sh.totals[0] = total & 0xffff; sh.totals[1] = (int)((uint32_t)total >> 16); }
   SEL_STAMP(5);
-  cluster_sync();  // totals visible; also: every CTA is past its last read of `stage`, so CTA 0's buffers are free
-  int gbase = 0, ebase = 0;
-  for (uint32_t c = 0; c < crank; ++c) {
-    gbase += (int)ld_cluster_u32(map_to_rank(&sh.totals[0], c));
-    ebase += (int)ld_cluster_u32(map_to_rank(&sh.totals[1], c));
-  }
   int gpos = gbase + (ex & 0xffff), epos = ebase + (int)((uint32_t)ex >> 16);
   const uint32_t rkey = map_to_rank(skey[0], 0), ridx = map_to_rank(sidx[0], 0);
-  float part_top = 0.f;
+  epos += count_gt;
+  const int eend = count_gt + need_eq;
 #pragma unroll
   for (int i = 0; i < E; ++i) {
-    if (i < nvalid) {
-      int pos = -1;
-      if ((int)keys[i] > thr_key) pos = gpos++;
-      else if ((int)keys[i] == thr_key) { if (epos < need_eq) pos = count_gt + epos; ++epos; }
-      if (pos >= 0) {
-        st_cluster_u16(rkey + 2u * pos, (uint16_t)keys[i]);
-        st_cluster_u32(ridx + 4u * pos, (uint32_t)(j0 + i));
-        part_top += T::to_float((uint16_t)key_to_float16_bits(keys[i]));
-      }
+    const int ky = (int)keys[i];
+    const bool is_gt = i < nvalid && ky >= thr_hi;
+    const bool is_eq = i < nvalid && !is_gt && ky >= thr_key;
+    const int pos = is_gt ? gpos : epos;
+    if (is_gt || (is_eq && epos < eend)) {
+      st_cluster_u16(rkey + 2u * pos, (uint16_t)ky);
+      st_cluster_u32(ridx + 4u * pos, (uint32_t)(j0 + i));
+    }
+    gpos += is_gt;
+    epos += is_eq;
+  }
+  if (out_sums) {   // exact threshold here (the bin shortcut is not taken when sums are requested)
+    float part_top = 0.f;
+    int e2 = ebase + (int)((uint32_t)ex >> 16);
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+      const int ky = (int)keys[i];
+      const bool is_gt = i < nvalid && ky >= thr_hi;
+      const bool is_eq = i < nvalid && ky == thr_key;
+      if (is_gt || (is_eq && e2 < need_eq)) part_top += T::to_float((uint16_t)key_to_float16_bits(keys[i]));
+      e2 += is_eq;
+    }
+    const float st = block_sum_f<kWarps>(part_top, sh.fsum);
+    if (tid == 0) {
+      st_cluster_f32(map_to_rank(&sh.cpsum[crank][0], 0), st);
+      st_cluster_f32(map_to_rank(&sh.cpsum[crank][1], 0), sum_all_cta);
     }
   }
-  if (out_sums) {
-    const float st = block_sum_f<kWarps>(part_top, sh.fsum);
-    if (tid == 0) { sh.psum[0] = st; sh.psum[1] = sum_all_cta; }
-  }
-  cluster_sync();  // all winners (and partial sums) have landed in / are readable by CTA 0
+  SEL_STAMP(13);
+  cluster_sync();  // all winners (and partial sums) have landed in CTA 0
+  if (crank != 0) { tl_end(tl); return; }   // nobody reads this CTA's shared memory any more: free the SM for the next kernel
 
   SEL_STAMP(6);
   // ---- 4. CTA 0: stable LSD radix sort by descending key, emit -------------------------------------
-  if (crank == 0) {
+  {
     if (out_sums && tid == 0) {
       float a = 0.f, bsum = 0.f;
-      for (uint32_t c = 0; c < csize; ++c) {
-        a += ld_cluster_f32(map_to_rank(&sh.psum[0], c));
-        bsum += ld_cluster_f32(map_to_rank(&sh.psum[1], c));
-      }
+      for (uint32_t c = 0; c < csize; ++c) { a += sh.cpsum[c][0]; bsum += sh.cpsum[c][1]; }
       out_sums[2 * row] = a;
       out_sums[2 * row + 1] = bsum;
     }
     int* wh = sh.whist[wid];
-    const int V = (k + kThreads - 1) / kThreads;          // slots per thread (<= 8)
+    const int V = (nsort + kThreads - 1) / kThreads;      // slots per thread (<= 8)
     const int per_warp = V * 32;                          // warp w owns elements [w*per_warp, (w+1)*per_warp)
     int cur = 0;
     // LSD radix sort on rk = kmax - key (ascending rk == descending key); the winners' keys usually
@@ -409,7 +522,7 @@ topk_cluster_kernel(const uint16_t* __restrict__ scores, int n, int kernel_size,
       // per-warp digit totals (elements of a warp's run are visited in order, so ranks are stable)
       for (int v = 0; v < V; ++v) {
         const int o = wid * per_warp + v * 32 + lane;
-        if (o < k) atomicAdd(&wh[((kmax - (int)skey[cur][o]) >> (8 * pass)) & 255], 1);
+        if (o < nsort) atomicAdd(&wh[((kmax - (int)skey[cur][o]) >> (8 * pass)) & 255], 1);
       }
       __syncthreads();
       // digit bases: thread t < 256 <-> digit t; exclusive scan over digits of the per-digit totals,
@@ -429,7 +542,7 @@ topk_cluster_kernel(const uint16_t* __restrict__ scores, int n, int kernel_size,
       // scatter in (warp, slot, lane) order with stable in-warp ranks
       for (int v = 0; v < V; ++v) {
         const int o = wid * per_warp + v * 32 + lane;
-        const bool in = o < k;
+        const bool in = o < nsort;
         const uint16_t key = in ? skey[cur][o] : (uint16_t)0;
         const uint32_t idx = in ? sidx[cur][o] : 0u;
         // lanes past the end use the last digit: they rank after every real element of the warp's run
@@ -444,7 +557,6 @@ topk_cluster_kernel(const uint16_t* __restrict__ scores, int n, int kernel_size,
     for (int r = tid; r < k; r += kThreads) out_idx[(int64_t)row * idx_stride + r] = (int32_t)sidx[cur][r];
   }
   SEL_STAMP(8);
-  cluster_sync();  // keep every CTA's shared memory alive until CTA 0 has read the partial sums
   tl_end(tl);
 }
 
@@ -511,6 +623,8 @@ static int dispatch_pool(int pool, const void* scores, int rows, int n, int kern
 
 #ifdef KVC_TRACE
 extern "C" int kvc_debug_sel_trace(long long* out) { return (int)cudaMemcpyFromSymbol(out, cl::g_sel_trace, sizeof(long long) * 16); }
+extern "C" int kvc_debug_sel_tail(long long* out) { return (int)cudaMemcpyFromSymbol(out, cl::g_sel_tail, sizeof(long long) * 16); }
+extern "C" int kvc_debug_sel_gt(long long* out) { return (int)cudaMemcpyFromSymbol(out, cl::g_sel_gt, sizeof(long long) * 8); }
 #endif
 
 // Returns 1 when the shape is outside what the cluster kernel covers (caller falls back).
