@@ -472,7 +472,7 @@ window_score_dyn_kernel(const __grid_constant__ CUtensorMap tmap_k, const Params
               const int head = head0 + h;
               if (head < p.groups) {
                 float sum = acc[h].x + acc[h].y;
-                if (p.reduce_mean) sum = sum / (float)p.w;
+                if (p.reduce_mean) sum = div_exact(sum, (float)p.w, 1.0f / (float)p.w);
                 p.out[((int64_t)VSEL(ub, v) * p.Hq + VSEL(ukvh, v) * p.groups + head) * nscore + key] = T::round1(sum);
               }
             }

@@ -534,7 +534,7 @@ window_score_fused_kernel(const __grid_constant__ CUtensorMap tmap_k, const Para
           const int head = (rb * 128 + wg * 32) / W + h;
           if (head < p.groups) {
             float s = acc[h].x + acc[h].y;
-            if (p.reduce_mean) s = s / (float)p.w;
+            if (p.reduce_mean) s = div_exact(s, (float)p.w, 1.0f / (float)p.w);
             p.out[((int64_t)b * p.Hq + kvh * p.groups + head) * nscore + key] = T::round1(s);
           }
         }
@@ -853,7 +853,7 @@ window_score_half_kernel(const __grid_constant__ CUtensorMap tmap_k, const Param
             const int head = col0 / W + h;
             if (head < p.groups) {
               float sum = acc[h].x + acc[h].y;
-              if (p.reduce_mean) sum = sum / (float)p.w;
+              if (p.reduce_mean) sum = div_exact(sum, (float)p.w, 1.0f / (float)p.w);
               p.out[((int64_t)b * p.Hq + kvh * p.groups + head) * nscore + key] = T::round1(sum);
             }
           }

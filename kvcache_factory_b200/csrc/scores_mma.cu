@@ -281,7 +281,7 @@ window_score_mma_kernel(const ScoreParams p) {
         if (head < p.groups && key < nscore) {
           float s = 0.f;
           for (int m = 0; m < mt_per_head; ++m) s += cs[(hl * mt_per_head + m) * kTileN + kk];
-          if (p.reduce_mean) s = s / (float)p.w;
+          if (p.reduce_mean) s = div_exact(s, (float)p.w, 1.0f / (float)p.w);
           p.out[((int64_t)b * p.Hq + kvh * p.groups + head) * nscore + key] = T::round1(s);
         }
       }

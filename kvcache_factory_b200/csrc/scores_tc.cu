@@ -424,7 +424,7 @@ window_score_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const Params 
             const int head = rb * kHeadsPerBlk + h;
             if (head < p.groups) {
               float s = acc[h].x + acc[h].y;
-              if (p.reduce_mean) s = s / (float)p.w;
+              if (p.reduce_mean) s = div_exact(s, (float)p.w, 1.0f / (float)p.w);
               p.out[((int64_t)b * p.Hq + kvh * p.groups + head) * nscore + key] = T::round1(s);
             }
           }

@@ -98,7 +98,7 @@ __device__ __forceinline__ uint32_t pooled_bits(const uint16_t* __restrict__ row
     const int p = j + t;
     if (p >= 0 && p < n) s += T::to_float(row[p]);
   }
-  return T::round1(s / (float)kernel_size);
+  return T::round1(div_exact(s, (float)kernel_size, 1.0f / (float)kernel_size));
 }
 
 template <typename T>
