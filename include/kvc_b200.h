@@ -205,6 +205,24 @@ int kvc_adakv_allocate(const void* pooled, const float* sums, int H, int n, int 
                        int w, int32_t* out_cap, int32_t* out_head_lens, int32_t* out_cu_klen,
                        void* workspace, size_t workspace_bytes, void* stream);
 
+/* The whole AdaKV prefill update_kv (AdaKVCluster.update_kv, pyramidkv/pyramidkv_utils.py:700-757) in ONE
+ * call: window-mean scores -> pooled scores + ratio sums -> global allocation -> read of the capacities (the
+ * reference synchronises at the same point, :718) -> per-head top-cap_h -> varlen gather.  B = 1 (:724).
+ * out_k / out_v: flattened [out_rows, d] buffers sized by the caller with an upper bound
+ * (H*(base_capacity+w) + H rows always suffices); the rows actually used are returned in *out_klen_sum.
+ * host_cap: H ints of (preferably pinned) host memory; max_cap_bound: widest index row the workspace is sized
+ * for (KVC_ERR_WORKSPACE if a head's capacity exceeds it: retry with a larger bound).  offsets (optional,
+ * 3 entries): byte offsets of the scores [H,L-w], pooled scores [H,L-w] and indices [H,*out_max_cap] in the
+ * workspace.  Synchronises `stream` once. */
+size_t kvc_adakv_prefill_workspace_bytes(int Hq, int Hkv, int L, int d, int w, int max_cap_bound);
+int kvc_adakv_prefill(const void* q, int64_t q_sh, int64_t q_sl, const void* k, int64_t k_sh, int64_t k_sl,
+                      const void* v, int64_t v_sh, int64_t v_sl, int Hq, int Hkv, int L, int d, int w,
+                      int dtype, int kernel_size, int pool, int base_capacity, float one_minus_floor,
+                      int floor_capacity, int normalize, int score_impl, void* out_k, void* out_v,
+                      int64_t out_rows, int32_t* out_cap, int32_t* out_head_lens, int32_t* out_cu_klen,
+                      int32_t* host_cap, int max_cap_bound, void* workspace, size_t workspace_bytes,
+                      int* out_max_cap, int64_t* out_klen_sum, size_t* offsets, void* stream);
+
 /* Multi-GPU building block of the same allocation (one KV-head shard per GPU):
  * out_hist int32[H,65536] = histogram of each local head's ratio-normalised scores over an
  * order-preserving 16-bit key (key of +0.0 is 0x8000; larger value -> larger key).  The host sums it

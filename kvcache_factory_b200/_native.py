@@ -8,6 +8,8 @@ the call raises.
 from __future__ import annotations
 
 import ctypes
+
+import numpy as np
 import os
 from ctypes import c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p, POINTER
 
@@ -54,6 +56,10 @@ _SIGNATURES = {
     "kvc_adakv_allocate_workspace_bytes": (c_size_t, [_i] * 2),
     "kvc_adakv_allocate": (c_int, [_p, _p, _i, _i, _i, _i, c_float, _i, _i, _i, _p, _p, _p, _p, c_size_t, _p]),
     "kvc_adakv_key_histogram": (c_int, [_p, _p, _i, _i, _i, _i, _p, _p]),
+    "kvc_adakv_prefill_workspace_bytes": (c_size_t, [_i] * 6),
+    "kvc_adakv_prefill": (c_int, [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _i, _i, _i, _i, _i, _i, _i, _i, _i,
+                                  c_float, _i, _i, _i, _p, _p, _i64, _p, _p, _p, _p, _i, _p, c_size_t,
+                                  POINTER(c_int), POINTER(c_int64), POINTER(c_size_t), _p]),
     "kvc_update_flatten_view": (c_int, [_p, _p, _p, _p, _p, _i, _i, _i, _i64, _p]),
     "kvc_append_rows": (c_int, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p]),
     "kvc_flatten_regrow": (c_int, [_p, _p, _p, _p, _p, _i, _i, _i, _i64, _p]),
@@ -392,6 +398,61 @@ def adakv_allocate(pooled: torch.Tensor, sums: torch.Tensor, base_capacity: int,
             int(base_capacity * floor_ratio), int(bool(normalize)), window_size,
             cap.data_ptr(), head_lens.data_ptr(), cu_klen.data_ptr(), ws.data_ptr(), ws.numel(), _stream(dev)))
     return cap, head_lens, cu_klen
+
+
+_pinned_caps = {}
+
+
+def adakv_prefill(query_states: torch.Tensor, key_states: torch.Tensor, value_states: torch.Tensor, window_size: int,
+                  kernel_size: int, pooling, base_capacity: int, floor_ratio: float, normalize: bool,
+                  impl: int = IMPL_AUTO, want_debug: bool = False):
+    """``AdaKVCluster.update_kv`` in ONE library call (scores, allocation, capacity read, select, varlen gather).
+    Returns (flat_k, flat_v, cap, head_lens, cu_klen, max_cap, klen_sum, debug)."""
+    dev = _require_cuda(query_states, key_states, value_states)
+    B, Hkv, L, d = key_states.shape
+    H = query_states.shape[1]
+    if B != 1:
+        raise AssertionError("AdaKV's flattened cache is defined for batch 1")      # pyramidkv_utils.py:724
+    if query_states.dtype != key_states.dtype or value_states.dtype != key_states.dtype:
+        raise TypeError("query, key and value dtypes differ")
+    e = key_states.element_size()
+    k = _rowmajor_last(key_states, 16 // e)
+    v = _rowmajor_last(value_states, 16 // e)
+    q = _rowmajor_last(query_states, 8 if d == 128 else 2)
+    w, n = window_size, L - window_size
+    out_rows = H * (base_capacity + w) + H            # sum of round(count*(1-f) + int(base*f)) <= H*base + H/2
+    flat_k = torch.empty((out_rows, d), dtype=k.dtype, device=dev)
+    flat_v = torch.empty_like(flat_k)
+    cap = torch.empty(H, dtype=torch.int32, device=dev)
+    head_lens = torch.empty(H, dtype=torch.int32, device=dev)
+    cu_klen = torch.empty(H + 1, dtype=torch.int32, device=dev)
+    host = _pinned_caps.get((dev.index, H))
+    if host is None:
+        host = _pinned_caps[(dev.index, H)] = torch.empty(H, dtype=torch.int32).pin_memory()
+    one_minus_floor = float(np.float32(1 - floor_ratio))                          # as torch evaluates it (:719)
+    bound = n    # index rows and select scratch sized for the widest possible head: workspace bytes, not work
+    with torch.cuda.device(dev):
+        key = ("adakv", dev.index, H, Hkv, L, d, w, bound)
+        nbytes = _ws_bytes_cache.get(key)
+        if nbytes is None:
+            nbytes = _ws_bytes_cache[key] = max(256, lib().kvc_adakv_prefill_workspace_bytes(H, Hkv, L, d, w, bound))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        mc, ks = c_int(0), c_int64(0)
+        offs = (c_size_t * 3)()
+        _check("kvc_adakv_prefill", lib().kvc_adakv_prefill(
+            q.data_ptr(), q.stride(1), q.stride(2), k.data_ptr(), k.stride(1), k.stride(2),
+            v.data_ptr(), v.stride(1), v.stride(2), H, Hkv, L, d, w, dtype_code(k.dtype), kernel_size,
+            pool_code(pooling), base_capacity, one_minus_floor, int(base_capacity * floor_ratio),
+            int(bool(normalize)), impl, flat_k.data_ptr(), flat_v.data_ptr(), out_rows, cap.data_ptr(),
+            head_lens.data_ptr(), cu_klen.data_ptr(), host.data_ptr(), bound, ws.data_ptr(), nbytes,
+            ctypes.byref(mc), ctypes.byref(ks), offs, _stream(dev)))
+    max_cap, klen_sum = mc.value, ks.value
+    debug = None
+    if want_debug:
+        debug = dict(scores=ws[offs[0]: offs[0] + H * n * e].view(k.dtype).view(1, H, n),
+                     pooled=ws[offs[1]: offs[1] + H * n * e].view(k.dtype).view(1, H, n), cap=cap,
+                     indices=ws[offs[2]: offs[2] + H * max_cap * 4].view(torch.int32).view(H, max_cap))
+    return flat_k[:klen_sum], flat_v[:klen_sum], cap, head_lens, cu_klen, max_cap, klen_sum, debug
 
 
 def adakv_key_histogram(pooled: torch.Tensor, sums: torch.Tensor, normalize: bool) -> torch.Tensor:

@@ -49,12 +49,16 @@ static AdaWorkspace carve(void* ws, int H, int n) {
   return a;
 }
 
+// Rows are cut into chunks of kAdaChunk scores, one CTA each (grid = chunks x heads: 256 CTAs at 32 x 64K instead of
+// one CTA per head); a CTA's shared-memory histogram is merged into the head's zero-initialised global one.
+constexpr int kAdaChunk = 8 * kAdaThreads;
+
 template <typename T>
 __global__ void __launch_bounds__(kAdaThreads)
 ada_phase1_kernel(const uint16_t* __restrict__ pooled, const float* __restrict__ sums, int n, int normalize,
                   uint16_t* __restrict__ akeys, int* __restrict__ hist1) {
   __shared__ int hist[kAdaBins];
-  const int h = blockIdx.x, tid = threadIdx.x;
+  const int h = blockIdx.y, tid = threadIdx.x;
   for (int i = tid; i < kAdaBins; i += kAdaThreads) hist[i] = 0;
   __syncthreads();
   // ratio_weight = sum(top base) / sum(all), each rounded to the model dtype (:710)
@@ -64,15 +68,21 @@ ada_phase1_kernel(const uint16_t* __restrict__ pooled, const float* __restrict__
     ratio = T::to_float(T::round1(top / all));
   }
   const uint16_t* row = pooled + (int64_t)h * n;
-  for (int j = tid; j < n; j += kAdaThreads) {
-    uint32_t bits = row[j];
-    if (normalize) bits = T::round1(T::to_float((uint16_t)bits) * ratio);  // :711
-    const uint32_t key = float16_bits_to_key(bits);
-    akeys[(int64_t)h * n + j] = (uint16_t)key;
-    atomicAdd(&hist[key >> 4], 1);
+  const int j0 = blockIdx.x * kAdaChunk;
+#pragma unroll
+  for (int u = 0; u < kAdaChunk / kAdaThreads; ++u) {
+    const int j = j0 + u * kAdaThreads + tid;
+    if (j < n) {
+      uint32_t bits = row[j];
+      if (normalize) bits = T::round1(T::to_float((uint16_t)bits) * ratio);  // :711
+      const uint32_t key = float16_bits_to_key(bits);
+      akeys[(int64_t)h * n + j] = (uint16_t)key;
+      atomicAdd(&hist[key >> 4], 1);
+    }
   }
   __syncthreads();
-  for (int i = tid; i < kAdaBins; i += kAdaThreads) hist1[(int64_t)h * kAdaBins + i] = hist[i];
+  for (int i = tid; i < kAdaBins; i += kAdaThreads)
+    if (hist[i]) atomicAdd(&hist1[(int64_t)h * kAdaBins + i], hist[i]);
 }
 
 // Sum per-head histograms and find the bin where the descending running count reaches K.
@@ -136,23 +146,30 @@ ada_phase3_kernel(const uint16_t* __restrict__ akeys, const int* __restrict__ hi
                   int* __restrict__ hist2, int* __restrict__ above) {
   __shared__ int h2[16];
   __shared__ int s_above;
-  const int h = blockIdx.x, tid = threadIdx.x;
+  const int h = blockIdx.y, tid = threadIdx.x;
   const int thr_bin = hdr->thr_bin;
   if (tid < 16) h2[tid] = 0;
   if (tid == 0) s_above = 0;
   __syncthreads();
-  int a = 0;
-  for (int i = thr_bin + 1 + tid; i < kAdaBins; i += kAdaThreads) a += hist1[(int64_t)h * kAdaBins + i];
+  if (blockIdx.x == 0) {   // the head's count above the threshold bin, once
+    int a = 0;
+    for (int i = thr_bin + 1 + tid; i < kAdaBins; i += kAdaThreads) a += hist1[(int64_t)h * kAdaBins + i];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-  if ((tid & 31) == 0 && a) atomicAdd(&s_above, a);
-  for (int j = tid; j < n; j += kAdaThreads) {
-    const uint32_t key = akeys[(int64_t)h * n + j];
-    if ((int)(key >> 4) == thr_bin) atomicAdd(&h2[key & 15], 1);
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if ((tid & 31) == 0 && a) atomicAdd(&s_above, a);
+  }
+  const int j0 = blockIdx.x * kAdaChunk;
+#pragma unroll
+  for (int u = 0; u < kAdaChunk / kAdaThreads; ++u) {
+    const int j = j0 + u * kAdaThreads + tid;
+    if (j < n) {
+      const uint32_t key = akeys[(int64_t)h * n + j];
+      if ((int)(key >> 4) == thr_bin) atomicAdd(&h2[key & 15], 1);
+    }
   }
   __syncthreads();
-  if (tid < 16) hist2[h * 16 + tid] = h2[tid];
-  if (tid == 0) above[h] = s_above;
+  if (tid < 16 && h2[tid]) atomicAdd(&hist2[h * 16 + tid], h2[tid]);
+  if (tid == 0 && blockIdx.x == 0) above[h] = s_above;
 }
 
 // One warp: lane <-> head (32 heads per round, carried totals across rounds), tiny tables.
@@ -226,14 +243,17 @@ int adakv_allocate(const void* pooled, const float* sums, int H, int n, int dtyp
   KVC_REQUIRE((int64_t)H * base_capacity <= (int64_t)H * n, KVC_ERR_ARG, "base capacity exceeds row length");
   AdaWorkspace a = carve(workspace, H, n);
   const int K = H * base_capacity;
+  const dim3 grid((n + kAdaChunk - 1) / kAdaChunk, H);
+  // hist1 and hist2 are adjacent in the workspace: one memset zeroes both accumulation targets
+  KVC_CUDA_TRY(cudaMemsetAsync(a.hist1, 0, (size_t)((char*)a.above - (char*)a.hist1), stream));
   if (dtype == KVC_BF16)
-    ada_phase1_kernel<Bf16><<<H, kAdaThreads, 0, stream>>>((const uint16_t*)pooled, sums, n, normalize, a.akeys, a.hist1);
+    ada_phase1_kernel<Bf16><<<grid, kAdaThreads, 0, stream>>>((const uint16_t*)pooled, sums, n, normalize, a.akeys, a.hist1);
   else
-    ada_phase1_kernel<Fp16><<<H, kAdaThreads, 0, stream>>>((const uint16_t*)pooled, sums, n, normalize, a.akeys, a.hist1);
+    ada_phase1_kernel<Fp16><<<grid, kAdaThreads, 0, stream>>>((const uint16_t*)pooled, sums, n, normalize, a.akeys, a.hist1);
   if (int rc = launch_status("ada_phase1_kernel")) return rc;
   ada_phase2_kernel<<<1, kAdaThreads, 0, stream>>>(a.hist1, H, K, a.hdr);
   if (int rc = launch_status("ada_phase2_kernel")) return rc;
-  ada_phase3_kernel<<<H, kAdaThreads, 0, stream>>>(a.akeys, a.hist1, n, a.hdr, a.hist2, a.above);
+  ada_phase3_kernel<<<grid, kAdaThreads, 0, stream>>>(a.akeys, a.hist1, n, a.hdr, a.hist2, a.above);
   if (int rc = launch_status("ada_phase3_kernel")) return rc;
   ada_phase4_kernel<<<1, 32, 0, stream>>>(a.hist2, a.above, H, n, K, one_minus_floor, floor_capacity, w, a.hdr, out_cap,
                                           out_head_lens, out_cu_klen);

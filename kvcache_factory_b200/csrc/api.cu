@@ -336,6 +336,85 @@ int kvc_adakv_allocate(const void* pooled, const float* sums, int H, int n, int 
                         out_cap, out_head_lens, out_cu_klen, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
+// ---- AdaKV prefill in one call -------------------------------------------------------------------------------------
+// Workspace layout: scores | pooled | sums | indices | scoring ws | select ws | allocation ws (each 256-aligned).
+struct AdaLayout { size_t scores, pooled, sums, idx, ws_scores, ws_select, ws_alloc, total, sc_ws, sel_ws, al_ws; };
+static AdaLayout ada_layout(int Hq, int Hkv, int L, int d, int w, int max_cap_bound) {
+  AdaLayout a{};
+  const size_t n = (size_t)(L - w);
+  size_t off = 0;
+  a.scores = off; off += align256((size_t)Hq * n * 2);
+  a.pooled = off; off += align256((size_t)Hq * n * 2);
+  a.sums = off; off += align256((size_t)Hq * 2 * sizeof(float));
+  a.idx = off; off += align256((size_t)Hq * (size_t)max_cap_bound * 4);
+  a.sc_ws = align256(kvc_window_scores_workspace_bytes(1, Hq, Hkv, L, d, w)) + 256;
+  a.sel_ws = align256(pool_topk_workspace_bytes(Hq, (int)n, max_cap_bound)) + 256;
+  a.al_ws = align256(adakv_allocate_workspace_bytes(Hq, (int)n)) + 256;
+  a.ws_scores = off; off += a.sc_ws;
+  a.ws_select = off; off += a.sel_ws;
+  a.ws_alloc = off; off += a.al_ws;
+  a.total = off;
+  return a;
+}
+
+size_t kvc_adakv_prefill_workspace_bytes(int Hq, int Hkv, int L, int d, int w, int max_cap_bound) {
+  if (Hq <= 0 || Hkv <= 0 || Hq % Hkv || L <= w || w <= 0 || max_cap_bound <= 0) return 0;
+  return ada_layout(Hq, Hkv, L, d, w, max_cap_bound).total;
+}
+
+int kvc_adakv_prefill(const void* q, int64_t q_sh, int64_t q_sl, const void* k, int64_t k_sh, int64_t k_sl, const void* v,
+                      int64_t v_sh, int64_t v_sl, int Hq, int Hkv, int L, int d, int w, int dtype, int kernel_size,
+                      int pool, int base_capacity, float one_minus_floor, int floor_capacity, int normalize,
+                      int score_impl, void* out_k, void* out_v, int64_t out_rows, int32_t* out_cap,
+                      int32_t* out_head_lens, int32_t* out_cu_klen, int32_t* host_cap, int max_cap_bound,
+                      void* workspace, size_t workspace_bytes, int* out_max_cap, int64_t* out_klen_sum,
+                      size_t* offsets, void* stream) {
+  if (int rc = check_device()) return rc;
+  if (int rc = check_shape(1, Hq, Hkv, L, d, w, dtype)) return rc;
+  KVC_REQUIRE(q && k && v && out_k && out_v && out_cap && out_head_lens && out_cu_klen && host_cap && workspace &&
+                  out_max_cap && out_klen_sum,
+              KVC_ERR_ARG, "null pointer argument");
+  const int n = L - w;
+  KVC_REQUIRE(base_capacity > 0 && base_capacity <= n, KVC_ERR_ARG, "base_capacity=%d outside (0, L-w=%d]", base_capacity, n);
+  KVC_REQUIRE(max_cap_bound >= base_capacity && max_cap_bound <= n, KVC_ERR_ARG, "max_cap_bound=%d outside [base_capacity, L-w]",
+              max_cap_bound);
+  KVC_REQUIRE(pool == KVC_POOL_AVG || pool == KVC_POOL_MAX, KVC_ERR_ARG, "Pooling method not supported (pool=%d)", pool);
+  const AdaLayout a = ada_layout(Hq, Hkv, L, d, w, max_cap_bound);
+  KVC_REQUIRE(workspace_bytes >= a.total, KVC_ERR_WORKSPACE, "adakv_prefill workspace: have %zu need %zu", workspace_bytes, a.total);
+  char* ws = (char*)workspace;
+  if (offsets) { offsets[0] = a.scores; offsets[1] = a.pooled; offsets[2] = a.idx; }
+  float* sums = (float*)(ws + a.sums);
+  int32_t* idx = (int32_t*)(ws + a.idx);
+  cudaStream_t st = (cudaStream_t)stream;
+  // window-mean scores -> pooled scores + (top-base, all) sums -> capacities (pyramidkv_utils.py:647-672, 706-719)
+  if (int rc = kvc_window_scores(q, 0, q_sh, q_sl, k, 0, k_sh, k_sl, 1, Hq, Hkv, L, d, w, dtype, KVC_REDUCE_MEAN, ws + a.scores,
+                                 ws + a.ws_scores, a.sc_ws, score_impl, stream))
+    return rc;
+  if (int rc = kvc_pool_topk(ws + a.scores, Hq, n, dtype, kernel_size, pool, base_capacity, nullptr, nullptr, base_capacity,
+                             ws + a.pooled, sums, ws + a.ws_select, a.sel_ws, stream))
+    return rc;
+  if (int rc = kvc_adakv_allocate(ws + a.pooled, sums, Hq, n, dtype, base_capacity, one_minus_floor, floor_capacity, normalize, w,
+                                  out_cap, out_head_lens, out_cu_klen, ws + a.ws_alloc, a.al_ws, stream))
+    return rc;
+  // the reference reads the capacities back here as well (:718); everything after it is sized by them
+  KVC_CUDA_TRY(cudaMemcpyAsync(host_cap, out_cap, (size_t)Hq * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  KVC_CUDA_TRY(cudaStreamSynchronize(st));
+  int max_cap = 0;
+  int64_t klen_sum = (int64_t)Hq * w;
+  for (int h = 0; h < Hq; ++h) { max_cap = host_cap[h] > max_cap ? host_cap[h] : max_cap; klen_sum += host_cap[h]; }
+  *out_max_cap = max_cap;
+  *out_klen_sum = klen_sum;
+  KVC_REQUIRE(max_cap <= max_cap_bound, KVC_ERR_WORKSPACE, "largest head capacity %d exceeds max_cap_bound %d", max_cap, max_cap_bound);
+  KVC_REQUIRE(klen_sum <= out_rows, KVC_ERR_WORKSPACE, "flattened cache needs %lld rows, output holds %lld", (long long)klen_sum,
+              (long long)out_rows);
+  if (max_cap > 0)
+    if (int rc = kvc_pool_topk(ws + a.scores, Hq, n, dtype, kernel_size, pool, max_cap, out_cap, idx, max_cap, nullptr, nullptr,
+                               ws + a.ws_select, a.sel_ws, stream))
+      return rc;
+  return kvc_gather_varlen(k, k_sh, k_sl, v, v_sh, v_sl, idx, max_cap, out_cap, out_cu_klen, Hq, Hkv, L, d, w, max_cap, 2, out_k,
+                           out_v, stream);
+}
+
 int kvc_adakv_key_histogram(const void* pooled, const float* sums, int H, int n, int dtype, int normalize,
                             int32_t* out_hist, void* stream) {
   if (int rc = check_device()) return rc;

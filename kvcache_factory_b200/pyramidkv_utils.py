@@ -425,6 +425,9 @@ class L2NormCluster:
         return out
 
 
+_CONST_META = {}
+
+
 class AdaKVCluster:
     """Reference ``AdaKVCluster`` (``pyramidkv_utils.py:622-757``): head-adaptive budgets, flattened
     ``[sum_h len_h, d]`` cache plus the varlen metadata its decode path consumes
@@ -432,6 +435,7 @@ class AdaKVCluster:
 
     keep_debug = False
     score_impl = N.IMPL_AUTO
+    fused_call = True          # whole update_kv in one library call (kvc_adakv_prefill); False = the five separate calls
 
     def __init__(self, window_size=32, kernel_size=7, pooling='maxpool', max_capacity_prompt=None, floor=None,
                  normalize=None, layer_idx=None, num_hidden_layers=None):
@@ -469,11 +473,17 @@ class AdaKVCluster:
         self.max_seqlen_k = max_seqlen_k
         self.cu_klen = cu_klen
         self.cu_headlens = cu_klen[1:].clone()
-        self.layer_qlens = torch.ones(num_heads, dtype=torch.int32, device=device)
         self.qlen_sum = num_heads
-        self.cu_qlen = torch.arange(0, num_heads + 1, dtype=torch.int32, device=device)
-        self.cu_offset = torch.arange(0, num_heads + 1, dtype=torch.int32, device=device)
-        self.cu_head_offset = torch.arange(1, num_heads + 1, dtype=torch.int32, device=device)
+        # the four constant tables are never written by any consumer: built once per (device, head count) instead of
+        # four tiny kernel launches per layer
+        key = (torch.device(device), num_heads)
+        const = _CONST_META.get(key)
+        if const is None:
+            const = _CONST_META[key] = (torch.ones(num_heads, dtype=torch.int32, device=device),
+                                        torch.arange(0, num_heads + 1, dtype=torch.int32, device=device),
+                                        torch.arange(0, num_heads + 1, dtype=torch.int32, device=device),
+                                        torch.arange(1, num_heads + 1, dtype=torch.int32, device=device))
+        self.layer_qlens, self.cu_qlen, self.cu_offset, self.cu_head_offset = const
 
     def update_kv(self, key_states, query_states, value_states):
         device = key_states.device
@@ -491,6 +501,17 @@ class AdaKVCluster:
             k_all, v_all = N.gather_dense(key_states, value_states, None, num_heads, n, w)
             return k_all.reshape(-1, head_dim), v_all.reshape(-1, head_dim)
         assert bsz == 1                                              # :724
+
+        if self.fused_call:
+            # one library call for the whole layer (scores, allocation, the capacity read the reference has at :718,
+            # select, varlen gather): the eager path is bound by host launch overhead, not by the kernels
+            flat_k, flat_v, cap, head_lens, cu_klen, max_cap, klen_sum, dbg = N.adakv_prefill(
+                query_states, key_states, value_states, w, self.kernel_size, self.pooling, self.base_capacity,
+                self.floor_ratio, bool(self.normalize), self.score_impl, want_debug=self.keep_debug)
+            self._init_metadata(device, num_heads, head_lens, cu_klen, klen_sum, max_cap + w)
+            if self.keep_debug:
+                self.debug = dbg
+            return flat_k, flat_v
 
         scores = N.window_scores(query_states, key_states, w, "mean", self.score_impl)
         # pooled scores + the per-head sums of (top-base, all) that the ratio normalisation needs (:706-711);

@@ -446,6 +446,37 @@ def test_fused_one_call_path_equals_three_calls(method, layout):
         SnapKVCluster(w, cap, 7, "medianpool").update_kv(Kd, Qd, Vd, None, 4)
 
 
+@pytest.mark.parametrize("pooling,floor,normalize", [("maxpool", 0.2, True), ("avgpool", 0.5, False)])
+@pytest.mark.parametrize("hf_layout", [False, True])
+def test_adakv_one_call_equals_separate_calls(pooling, floor, normalize, hf_layout):
+    """kvc_adakv_prefill (the default: one library call per AdaKV update_kv) against the five separate calls:
+    identical capacities, metadata and flattened rows."""
+    shape = Shape(1, 8, 2, 3001, 128)
+    w = 32
+    Q, K, V = make_qkv(shape, torch.bfloat16, layer_idx=2, dist="peaked", window=w)
+    Qd, Kd, Vd = Q.to(dev()), K.to(dev()), V.to(dev())
+    if hf_layout:
+        Qd = Qd.transpose(1, 2).contiguous().transpose(1, 2)
+        Kd = Kd.transpose(1, 2).contiguous().transpose(1, 2)
+        Vd = Vd.transpose(1, 2).contiguous().transpose(1, 2)
+    mk = lambda: AdaKVCluster(window_size=w, kernel_size=7, pooling=pooling, max_capacity_prompt=256 + w, floor=floor,
+                              normalize=normalize, layer_idx=0, num_hidden_layers=4)
+    a, b = mk(), mk()
+    a.keep_debug = b.keep_debug = True
+    b.fused_call = False
+    Ka, Va = a.update_kv(Kd, Qd, Vd)
+    Kb, Vb = b.update_kv(Kd, Qd, Vd)
+    torch.cuda.synchronize()
+    assert Ka.shape == Kb.shape and Ka.is_contiguous() and torch.equal(Ka, Kb) and torch.equal(Va, Vb)
+    for attr in ("head_lens", "cu_klen", "cu_headlens"):
+        assert torch.equal(getattr(a, attr), getattr(b, attr)), attr
+    assert (a.klen_sum, a.max_seqlen_k) == (b.klen_sum, b.max_seqlen_k)
+    assert torch.equal(a.debug["pooled"].view(-1), b.debug["pooled"].view(-1))
+    caps = (a.head_lens - w).tolist()
+    for h, c in enumerate(caps):      # entries past a head's capacity are unspecified
+        assert torch.equal(a.debug["indices"][h, :c], b.debug["indices"][h, :c]), h
+
+
 def test_repeated_layout_gives_same_result_as_unrepeated():
     shape = Shape(1, 8, 2, 600, 128)
     Q, K, V = make_qkv(shape, torch.bfloat16, layer_idx=4, dist="peaked", window=32)
