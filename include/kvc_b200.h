@@ -231,6 +231,16 @@ int kvc_adakv_prefill(const void* q, int64_t q_sh, int64_t q_sl, const void* k, 
 int kvc_adakv_key_histogram(const void* pooled, const float* sums, int H, int n, int dtype,
                             int normalize, int32_t* out_hist, void* stream);
 
+/* The same exchange on the two-level histograms the single-GPU allocation uses (16 KiB + 64 B all-reduces instead
+ * of 256 KiB): coarse = per-head 4096-bin histogram of key >> 4 (out_hist1 int32[H,4096]) and the normalised keys
+ * themselves (akeys uint16[H,n], scratch for the second phase); fine = per-head 16-bin histogram of the keys
+ * inside the threshold bin (*thr_bin: DEVICE int, so no host read sits between the phases) and the per-head count
+ * above that bin.  Reference anchor: the global top-(H*base) of pyramidkv/pyramidkv_utils.py:712-717. */
+int kvc_adakv_hist_coarse(const void* pooled, const float* sums, int H, int n, int dtype, int normalize,
+                          void* akeys, int32_t* out_hist1, void* stream);
+int kvc_adakv_hist_fine(const void* akeys, const int32_t* hist1, int H, int n, const int32_t* thr_bin,
+                        int32_t* out_hist2, int32_t* out_above, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Flattened-cache append — replaces tiny_api_cuda.update_flatten_view
  * csrc/csrc/cuda_api.cu:55-85 (kernel :11-53), called by DynamicCacheSplitHeadFlatten.update

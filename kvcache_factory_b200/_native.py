@@ -56,6 +56,8 @@ _SIGNATURES = {
     "kvc_adakv_allocate_workspace_bytes": (c_size_t, [_i] * 2),
     "kvc_adakv_allocate": (c_int, [_p, _p, _i, _i, _i, _i, c_float, _i, _i, _i, _p, _p, _p, _p, c_size_t, _p]),
     "kvc_adakv_key_histogram": (c_int, [_p, _p, _i, _i, _i, _i, _p, _p]),
+    "kvc_adakv_hist_coarse": (c_int, [_p, _p, _i, _i, _i, _i, _p, _p, _p]),
+    "kvc_adakv_hist_fine": (c_int, [_p, _p, _i, _i, _p, _p, _p, _p]),
     "kvc_adakv_prefill_workspace_bytes": (c_size_t, [_i] * 6),
     "kvc_adakv_prefill": (c_int, [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _i, _i, _i, _i, _i, _i, _i, _i, _i,
                                   c_float, _i, _i, _i, _p, _p, _i64, _p, _p, _p, _p, _i, _p, c_size_t,
@@ -465,6 +467,34 @@ def adakv_key_histogram(pooled: torch.Tensor, sums: torch.Tensor, normalize: boo
             pooled.contiguous().data_ptr(), sums.data_ptr(), H, n, dtype_code(pooled.dtype), int(bool(normalize)),
             hist.data_ptr(), _stream(dev)))
     return hist
+
+
+def adakv_hist_coarse(pooled: torch.Tensor, sums: torch.Tensor, normalize: bool):
+    """(akeys uint16 [H,n] as int16 storage, hist1 int32 [H,4096]): first counting phase of the AdaKV allocation."""
+    dev = _require_cuda(pooled, sums)
+    H, n = pooled.shape
+    akeys = torch.empty((H, n), dtype=torch.int16, device=dev)
+    hist1 = torch.empty((H, 4096), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _check("kvc_adakv_hist_coarse", lib().kvc_adakv_hist_coarse(
+            pooled.contiguous().data_ptr(), sums.data_ptr(), H, n, dtype_code(pooled.dtype), int(bool(normalize)),
+            akeys.data_ptr(), hist1.data_ptr(), _stream(dev)))
+    return akeys, hist1
+
+
+def adakv_hist_fine(akeys: torch.Tensor, hist1: torch.Tensor, thr_bin: torch.Tensor):
+    """(hist2 int32 [H,16], above int32 [H]) for the DEVICE scalar ``thr_bin`` (int32): second counting phase."""
+    dev = _require_cuda(akeys, hist1, thr_bin)
+    if thr_bin.dtype != torch.int32 or thr_bin.numel() != 1:
+        raise TypeError("thr_bin must be one int32 on the device")
+    H, n = akeys.shape
+    hist2 = torch.empty((H, 16), dtype=torch.int32, device=dev)
+    above = torch.empty(H, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _check("kvc_adakv_hist_fine", lib().kvc_adakv_hist_fine(
+            akeys.data_ptr(), hist1.data_ptr(), H, n, thr_bin.data_ptr(), hist2.data_ptr(), above.data_ptr(),
+            _stream(dev)))
+    return hist2, above
 
 
 def update_flatten_view(cache: torch.Tensor, state: torch.Tensor, headlens: torch.Tensor,

@@ -11,6 +11,8 @@
 //                         head_lens and the exclusive prefix cu_klen
 // In the multi-GPU layout (one KV-head shard per GPU) the two histogram sums are the only data
 // that has to cross GPUs (16 KiB + 64 B): see kvcache_factory_b200/sharding.py.
+#include <cstddef>
+
 #include "common.cuh"
 
 namespace kvc {
@@ -258,6 +260,31 @@ int adakv_allocate(const void* pooled, const float* sums, int H, int n, int dtyp
   ada_phase4_kernel<<<1, 32, 0, stream>>>(a.hist2, a.above, H, n, K, one_minus_floor, floor_capacity, w, a.hdr, out_cap,
                                           out_head_lens, out_cu_klen);
   return launch_status("ada_phase4_kernel");
+}
+
+}  // namespace kvc
+
+// ---- the two counting phases on their own (multi-GPU: the caller all-reduces between them) --------------------
+namespace kvc {
+
+int adakv_hist_coarse(const void* pooled, const float* sums, int H, int n, int dtype, int normalize, uint16_t* akeys,
+                      int32_t* hist1, cudaStream_t stream) {
+  const dim3 grid((n + kAdaChunk - 1) / kAdaChunk, H);
+  KVC_CUDA_TRY(cudaMemsetAsync(hist1, 0, (size_t)H * kAdaBins * sizeof(int32_t), stream));
+  if (dtype == KVC_BF16)
+    ada_phase1_kernel<Bf16><<<grid, kAdaThreads, 0, stream>>>((const uint16_t*)pooled, sums, n, normalize, akeys, hist1);
+  else
+    ada_phase1_kernel<Fp16><<<grid, kAdaThreads, 0, stream>>>((const uint16_t*)pooled, sums, n, normalize, akeys, hist1);
+  return launch_status("ada_phase1_kernel");
+}
+
+int adakv_hist_fine(const uint16_t* akeys, const int32_t* hist1, int H, int n, const int32_t* thr_bin, int32_t* hist2,
+                    int32_t* above, cudaStream_t stream) {
+  static_assert(offsetof(AdaHeader, thr_bin) == 0, "phase 3 reads the threshold bin through the header's first word");
+  const dim3 grid((n + kAdaChunk - 1) / kAdaChunk, H);
+  KVC_CUDA_TRY(cudaMemsetAsync(hist2, 0, (size_t)H * 16 * sizeof(int32_t), stream));
+  ada_phase3_kernel<<<grid, kAdaThreads, 0, stream>>>(akeys, hist1, n, reinterpret_cast<const AdaHeader*>(thr_bin), hist2, above);
+  return launch_status("ada_phase3_kernel");
 }
 
 }  // namespace kvc

@@ -41,6 +41,8 @@ int h2o_scores(const void*, int64_t, int64_t, int64_t, const void*, int64_t, int
                int, int, int, void*, void*, size_t, cudaStream_t);
 size_t adakv_allocate_workspace_bytes(int H, int n);
 int adakv_key_histogram(const void*, const float*, int, int, int, int, int32_t*, cudaStream_t);
+int adakv_hist_coarse(const void*, const float*, int, int, int, int, uint16_t*, int32_t*, cudaStream_t);
+int adakv_hist_fine(const uint16_t*, const int32_t*, int, int, const int32_t*, int32_t*, int32_t*, cudaStream_t);
 int adakv_allocate(const void*, const float*, int, int, int, int, float, int, int, int, int32_t*, int32_t*, int32_t*,
                    void*, size_t, cudaStream_t);
 
@@ -413,6 +415,23 @@ int kvc_adakv_prefill(const void* q, int64_t q_sh, int64_t q_sl, const void* k, 
       return rc;
   return kvc_gather_varlen(k, k_sh, k_sl, v, v_sh, v_sl, idx, max_cap, out_cap, out_cu_klen, Hq, Hkv, L, d, w, max_cap, 2, out_k,
                            out_v, stream);
+}
+
+int kvc_adakv_hist_coarse(const void* pooled, const float* sums, int H, int n, int dtype, int normalize, void* akeys,
+                          int32_t* hist1, void* stream) {
+  if (int rc = check_device()) return rc;
+  KVC_REQUIRE(pooled && akeys && hist1 && (sums || !normalize), KVC_ERR_ARG, "null pointer");
+  KVC_REQUIRE(H > 0 && n > 0, KVC_ERR_ARG, "H=%d n=%d", H, n);
+  KVC_REQUIRE(dtype == KVC_BF16 || dtype == KVC_FP16, KVC_ERR_UNSUPPORTED, "dtype %d", dtype);
+  return adakv_hist_coarse(pooled, sums, H, n, dtype, normalize, (uint16_t*)akeys, hist1, (cudaStream_t)stream);
+}
+
+int kvc_adakv_hist_fine(const void* akeys, const int32_t* hist1, int H, int n, const int32_t* thr_bin, int32_t* hist2,
+                        int32_t* above, void* stream) {
+  if (int rc = check_device()) return rc;
+  KVC_REQUIRE(akeys && hist1 && thr_bin && hist2 && above, KVC_ERR_ARG, "null pointer");
+  KVC_REQUIRE(H > 0 && n > 0, KVC_ERR_ARG, "H=%d n=%d", H, n);
+  return adakv_hist_fine((const uint16_t*)akeys, hist1, H, n, thr_bin, hist2, above, (cudaStream_t)stream);
 }
 
 int kvc_adakv_key_histogram(const void* pooled, const float* sums, int H, int n, int dtype, int normalize,

@@ -5,11 +5,14 @@ GQA group, so the shardable unit is ``(batch, kv_head)`` with its ``Hq/Hkv`` que
 PyramidKV, H2O and StreamingLLM need NO collective: each rank runs the ordinary cluster on the
 units it owns.  AdaKV has exactly one exchange: the global top-(H*base) over all heads' normalised
 scores (reference ``pyramidkv_utils.py:712-717``).  Scores are 16-bit floats, so that top-k is
-fully determined by a 65 536-bin histogram of an order-preserving key:
+fully determined by histograms of an order-preserving key, taken at the two levels the single-GPU
+allocation kernels use (``adakv.cu``):
 
-    local [H_local, 65536] histogram  (CUDA: kvc_adakv_key_histogram)
-      -> sum over local heads -> all_reduce(SUM)            one 256 KiB collective
-      -> threshold key T and #winners above it              (every rank, identical)
+    local [H_local, 4096] histogram of key >> 4   (CUDA: kvc_adakv_hist_coarse)
+      -> sum over local heads -> all_reduce(SUM)            16 KiB
+      -> threshold bin (device scalar, never read by the host)
+    local [H_local, 16] histogram inside that bin + per-head count above it   (kvc_adakv_hist_fine)
+      -> sum over local heads -> all_reduce(SUM)            64 B -> threshold key T
       -> all_gather of per-head (above, equal) counts       2*H_local int64 per rank
       -> ties at T go to the lowest GLOBAL head index first  (torch.topk leaves tie order unspecified)
       -> cap_h = round(count_h*(1-floor) + int(base*floor))  same ATen ops as the reference (:719)
@@ -46,31 +49,42 @@ def shard_qkv(query_states, key_states, value_states, world_size: int, rank: int
     return (query_states[:, s.start * g: s.stop * g], key_states[:, s], value_states[:, s])
 
 
-def adakv_caps_from_histograms(hist_local: torch.Tensor, total_heads: int, base_capacity: int, floor_ratio: float,
-                               row_len: int, group: Optional["dist.ProcessGroup"] = None,
-                               rank: int = 0, world_size: int = 1):
-    """Head capacities of this rank's heads from their key histograms.
+def adakv_caps_two_level(coarse, fine, total_heads: int, base_capacity: int, floor_ratio: float, row_len: int,
+                         group: Optional["dist.ProcessGroup"] = None, rank: int = 0, world_size: int = 1):
+    """Head capacities of this rank's heads from the two-level key histograms of ``adakv.cu``.
 
-    ``hist_local``: int [H_local, 65536].  Heads are laid out rank-major (rank r owns global heads
-    ``[r*H_local, (r+1)*H_local)``).  Returns (cap_local int32 [H_local], cap_all int32 [total_heads],
-    threshold key).  With world_size == 1 no collective is issued.
+    ``coarse() -> int [H_local, 4096]`` (histogram of ``key >> 4``); ``fine(thr_bin) -> (int [H_local, 16],
+    int [H_local])`` (histogram of ``key & 15`` inside bin ``thr_bin``, a one-element int32 tensor on the histograms'
+    device, and the count above that bin).  Heads are laid out rank-major.  Collectives (world_size > 1): all-reduce
+    of 4096 int32 (16 KiB), all-reduce of 16 int32, all-gather of 2 ints per head.  Nothing is read back to the host
+    between the phases.  Returns (cap_local int32 [H_local], cap_all int32 [total_heads], threshold key as a tensor).
     """
-    H_local = hist_local.shape[0]
+    K = total_heads * base_capacity
+    h1 = coarse()
+    H_local = h1.shape[0]
     if H_local * world_size != total_heads:
         raise ValueError("heads must be split evenly over the ranks")
-    K = total_heads * base_capacity
-    tot = hist_local.sum(dim=0, dtype=torch.int64)
+    dev = h1.device
+    tot1 = h1.sum(dim=0, dtype=torch.int32)
     if world_size > 1:
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=group)
-    # descending cumulative count: first key (from the top) at which it reaches K
-    csum = tot.flip(0).cumsum(0)
-    pos = int(torch.searchsorted(csum, torch.tensor([K], dtype=csum.dtype, device=csum.device)).item())
-    pos = min(pos, 65535)
-    thr = 65535 - pos
-    h64 = hist_local.to(torch.int64)
-    above = h64[:, thr + 1:].sum(dim=1)
-    equal = h64[:, thr]
-    mine = torch.stack([above, equal], dim=1).contiguous()
+        dist.all_reduce(tot1, op=dist.ReduceOp.SUM, group=group)
+    Kt = torch.tensor([K], dtype=torch.int64, device=dev)
+    desc1 = tot1.flip(0).to(torch.int64).cumsum(0)               # running count from the top bin down
+    pos1 = torch.searchsorted(desc1, Kt).clamp(max=4095)         # first bin (from the top) reaching K
+    thr_bin = (4095 - pos1).to(torch.int32)
+    above_bin = desc1[pos1] - tot1.flip(0)[pos1].to(torch.int64)  # keys in the bins above it
+    h2, above = fine(thr_bin)
+    tot2 = h2.sum(dim=0, dtype=torch.int32)
+    if world_size > 1:
+        dist.all_reduce(tot2, op=dist.ReduceOp.SUM, group=group)
+    desc2 = tot2.flip(0).to(torch.int64).cumsum(0) + above_bin
+    pos2 = torch.searchsorted(desc2, Kt).clamp(max=15)
+    thr_low = 15 - pos2                                          # low four bits of the threshold key
+    lows = torch.arange(16, device=dev)
+    h2l = h2.to(torch.int64)
+    gt = above.to(torch.int64) + (h2l * (lows > thr_low)).sum(dim=1)
+    eq = h2l.gather(1, thr_low.expand(H_local, 1)).squeeze(1)
+    mine = torch.stack([gt, eq], dim=1).contiguous()
     if world_size > 1:
         parts = [torch.empty_like(mine) for _ in range(world_size)]
         dist.all_gather(parts, mine, group=group)
@@ -78,14 +92,33 @@ def adakv_caps_from_histograms(hist_local: torch.Tensor, total_heads: int, base_
     else:
         allc = mine
     above_all, equal_all = allc[:, 0], allc[:, 1]
-    remaining = K - int(above_all.sum())
+    remaining = K - above_all.sum()
     before = equal_all.cumsum(0) - equal_all                      # ties claimed by lower global heads
     take = (remaining - before).clamp(min=0).minimum(equal_all)
     counts = above_all + take
     floor_capacity = int(base_capacity * floor_ratio)
     cap_all = torch.round(counts * (1 - floor_ratio) + floor_capacity).int().clamp(max=row_len)   # :719
     cap_local = cap_all[rank * H_local: (rank + 1) * H_local].contiguous()
-    return cap_local, cap_all, thr
+    return cap_local, cap_all, (thr_bin.to(torch.int64) * 16 + thr_low).squeeze(0)
+
+
+def adakv_caps_from_histograms(hist_local: torch.Tensor, total_heads: int, base_capacity: int, floor_ratio: float,
+                               row_len: int, group: Optional["dist.ProcessGroup"] = None,
+                               rank: int = 0, world_size: int = 1):
+    """The same from full-resolution histograms (``int [H_local, 65536]``, e.g. ``kvc_adakv_key_histogram`` or a CPU
+    bincount): the two levels are cut out of them.  Returns (cap_local, cap_all, threshold key as an int)."""
+    H_local = hist_local.shape[0]
+
+    def coarse():
+        return hist_local.view(H_local, 4096, 16).sum(dim=2)
+
+    def fine(thr_bin):
+        b = int(thr_bin)
+        return (hist_local[:, b * 16:(b + 1) * 16], hist_local[:, (b + 1) * 16:].sum(dim=1))
+
+    cap_local, cap_all, thr = adakv_caps_two_level(coarse, fine, total_heads, base_capacity, floor_ratio, row_len,
+                                                   group, rank, world_size)
+    return cap_local, cap_all, int(thr)
 
 
 class ShardedAdaKV:
@@ -108,9 +141,17 @@ class ShardedAdaKV:
         scores = N.window_scores(query_states, key_states, w, "mean", c.score_impl)
         idx_base, pooled, sums = N.pool_topk(scores, c.kernel_size, c.pooling, c.base_capacity,
                                              want_pooled=True, want_sums=True)
-        hist = N.adakv_key_histogram(pooled.view(heads_local, n), sums, bool(c.normalize))
-        cap, cap_all, _ = adakv_caps_from_histograms(hist, heads_local * self.world, c.base_capacity, c.floor_ratio,
-                                                     n, self.group, self.rank, self.world)
+        keys = {}
+
+        def coarse():
+            keys["akeys"], keys["hist1"] = N.adakv_hist_coarse(pooled.view(heads_local, n), sums, bool(c.normalize))
+            return keys["hist1"]
+
+        def fine(thr_bin):
+            return N.adakv_hist_fine(keys["akeys"], keys["hist1"], thr_bin)
+
+        cap, cap_all, _ = adakv_caps_two_level(coarse, fine, heads_local * self.world, c.base_capacity, c.floor_ratio,
+                                               n, self.group, self.rank, self.world)
         cap = cap.to(device=device, dtype=torch.int32)
         head_lens = cap + w
         cu_klen = torch.zeros(heads_local + 1, dtype=torch.int32, device=device)

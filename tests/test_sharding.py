@@ -119,6 +119,31 @@ def test_key_histogram_kernel_matches_cpu(normalize):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("normalize", [True, False])
+def test_two_level_histogram_kernels_match_cpu(normalize):
+    """kvc_adakv_hist_coarse / kvc_adakv_hist_fine (what ShardedAdaKV exchanges) against the 65 536-bin CPU histogram,
+    and the capacities they lead to against the full-resolution path."""
+    from kvcache_factory_b200 import _native
+    pooled, adaptive, cap_ref, base, floor = _case(normalize=normalize, L=9000, base=300)
+    H, n = adaptive.shape
+    dev = torch.device("cuda:0")
+    p = pooled[0].to(dev)
+    _, _, sums = _native.pool_topk(p, 1, None, base, want_sums=True)
+    full = _hist(adaptive)
+    akeys, h1 = _native.adakv_hist_coarse(p, sums, normalize)
+    assert torch.equal(h1.cpu().long(), full.view(H, 4096, 16).sum(2))
+    # (the oracle's normalised scores are sorted per head, as the reference sorts before normalising: compare as multisets)
+    assert np.array_equal(np.sort(akeys.cpu().numpy().view(np.uint16).astype(np.int64), axis=1), np.sort(_keys(adaptive), axis=1))
+    for b in (int(full.sum(0).view(4096, 16).sum(1).nonzero().max()), int(full.sum(0).view(4096, 16).sum(1).argmax())):
+        h2, above = _native.adakv_hist_fine(akeys, h1, torch.tensor([b], dtype=torch.int32, device=dev))
+        assert torch.equal(h2.cpu().long(), full[:, b * 16:(b + 1) * 16])
+        assert torch.equal(above.cpu().long(), full[:, (b + 1) * 16:].sum(1))
+    cap2, _, thr2 = sharding.adakv_caps_two_level(lambda: h1, lambda t: _native.adakv_hist_fine(akeys, h1, t), H, base, floor, n)
+    cap1, _, thr1 = sharding.adakv_caps_from_histograms(full, H, base, floor, n)
+    assert int(thr2) == thr1 and torch.equal(cap2.cpu(), cap1)
+
+
+@pytest.mark.gpu
 def test_sharded_adakv_world1_equals_cluster():
     from kvcache_factory_b200 import AdaKVCluster
     shape = Shape(1, 8, 2, 900, 128)
