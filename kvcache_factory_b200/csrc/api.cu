@@ -31,9 +31,10 @@ size_t window_scores_dyn_workspace_bytes(int B, int Hq, int Hkv, int L, int d, i
 int window_scores_dyn(const void*, int64_t, int64_t, int64_t, const void*, int64_t, int64_t, int64_t, int, int, int,
                       int, int, int, int, int, void*, void*, size_t, const float*, cudaStream_t);
 bool window_scores_fused_supported(int B, int Hq, int Hkv, int L, int d, int w);
+bool window_scores_split_preferred(int B, int Hq, int Hkv, int L, int d, int w);
 size_t window_scores_fused_workspace_bytes(int B, int Hq, int Hkv, int L, int d, int w);
 int window_scores_fused(const void*, int64_t, int64_t, int64_t, const void*, int64_t, int64_t, int64_t, int, int, int,
-                        int, int, int, int, int, void*, void*, size_t, bool, cudaStream_t);
+                        int, int, int, int, int, void*, void*, size_t, int, cudaStream_t);
 int window_scores_tc(const void*, int64_t, int64_t, int64_t, const void*, int64_t, int64_t, int64_t, int, int, int,
                      int, int, int, int, int, void*, void*, size_t, cudaStream_t);
 size_t h2o_scores_workspace_bytes(int B, int Hq, int Hkv, int L, int d, int w);
@@ -178,7 +179,9 @@ int kvc_window_scores(const void* q, int64_t q_sb, int64_t q_sh, int64_t q_sl, c
   // layer), the dynamically scheduled kernel for more units than SMs, then the two-launch tcgen05 kernel, then mma.sync
   if (impl == KVC_IMPL_TCGEN05_FUSED || impl == KVC_IMPL_TCGEN05_HALF || (impl == KVC_IMPL_AUTO && fused_ok && aligned))
     return window_scores_fused(q, q_sb, q_sh, q_sl, k, k_sb, k_sh, k_sl, B, Hq, Hkv, L, d, w, dtype, reduce, out_scores,
-                               workspace, workspace_bytes, impl == KVC_IMPL_TCGEN05_HALF, (cudaStream_t)stream);
+                               workspace, workspace_bytes,
+                               impl == KVC_IMPL_TCGEN05_HALF ? 1 : (impl == KVC_IMPL_AUTO && window_scores_split_preferred(B, Hq, Hkv, L, d, w) ? 2 : 0),
+                               (cudaStream_t)stream);
   if (impl == KVC_IMPL_TCGEN05_DYN || (impl == KVC_IMPL_AUTO && dyn_ok && aligned))
     return window_scores_dyn(q, q_sb, q_sh, q_sl, k, k_sb, k_sh, k_sl, B, Hq, Hkv, L, d, w, dtype, reduce, out_scores,
                              workspace, workspace_bytes, nullptr, (cudaStream_t)stream);

@@ -44,6 +44,7 @@ struct Params {
   int chunk_tiles, nchunks;
   float scale;
   int reduce_mean;
+  int rbs;              // half-footprint kernel: 128-row blocks (= units) per KV head
   float2* stats;        // [units][nchunks][RB*128]
   uint16_t* out;        // [B,Hq,L-w]
   unsigned long long* tl;  // developer timeline entry (TRACE builds), else nullptr
@@ -607,12 +608,17 @@ window_score_half_kernel(const __grid_constant__ CUtensorMap tmap_k, const Param
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int chunk = blockIdx.x, unit = blockIdx.y;
-  const int b = unit / p.Hkv, kvh = unit % p.Hkv;
+  // a unit is one 128-row block of a (batch, KV head): KV heads with more than 128 stacked window rows (70B: 8 x 32)
+  // are served as p.rbs units that read the same keys (the second one from L2)
+  const int rbi = unit % p.rbs, kvu = unit / p.rbs;
+  const int b = kvu / p.Hkv, kvh = kvu % p.Hkv;
+  const int head0 = rbi * (128 / W);                       // first head of the KV group in this row block
+  const int gl = min(128 / W, p.groups - head0);           // heads in this row block
   const int nscore = p.L - p.w;
   const int tile_begin = chunk * p.chunk_tiles;
   const int n1 = max(0, min(tile_begin + p.chunk_tiles, (p.L + kTile - 1) / kTile) - tile_begin);
   const int n2 = max(0, min(tile_begin + p.chunk_tiles, (nscore + kTile - 1) / kTile) - tile_begin);
-  const int nq = p.groups * p.w;
+  const int nq = gl * p.w;
   auto tile_of = [&](int it) { return it < n1 ? tile_begin + it : tile_begin + (n2 - 1 - (it - n1)); };
 
   const uint32_t q_s = base, k_s = base + SM::kQBytes, bar_s = base + SM::kBarOff;
@@ -698,8 +704,8 @@ window_score_half_kernel(const __grid_constant__ CUtensorMap tmap_k, const Param
       const int e = et + it * kHEpiThreads;
       const int r = e >> 4, c16 = e & 15;
       const int hl = r / W, i = r % W;
-      const bool ok = hl < p.groups;
-      const uint16_t* src = p.q + b * p.q_sb + (int64_t)(kvh * p.groups + (ok ? hl : 0)) * p.q_sh +
+      const bool ok = hl < gl;
+      const uint16_t* src = p.q + b * p.q_sb + (int64_t)(kvh * p.groups + head0 + (ok ? hl : 0)) * p.q_sh +
                             (int64_t)(nscore + i) * p.q_sl + c16 * 8;
       const uint32_t dst = q_s + (c16 >> 3) * kHalfBytes + r * 128 + (((c16 & 7) ^ (r & 7)) << 4);
       const int sz = ok ? 16 : 0;
@@ -711,7 +717,7 @@ window_score_half_kernel(const __grid_constant__ CUtensorMap tmap_k, const Param
     mbar_arrive(qbar);
 
     const uint32_t tcol = tmem_base + ((uint32_t)(quad * 32) << 16) + wg * kCols;
-    const bool dead_rows = __all_sync(0xffffffffu, r_loc / W >= p.groups);
+    const bool dead_rows = __all_sync(0xffffffffu, r_loc / W >= gl);
     // ---------------- pass 1 ----------------
     float m_run = -1e30f;
     float2 zacc[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
@@ -734,7 +740,7 @@ window_score_half_kernel(const __grid_constant__ CUtensorMap tmap_k, const Param
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty(buf));
       if (key0 + kCols > nscore) {
-        const int last_key = min(p.L - 1, r_loc / W < p.groups ? nscore + r_loc % W : p.L - 1);
+        const int last_key = min(p.L - 1, r_loc / W < gl ? nscore + r_loc % W : p.L - 1);
         p1_chunk<T, true>(va, scale, m_run, zacc, key0, last_key);
         if constexpr (kChunks == 2) p1_chunk<T, true>(vb, scale, m_run, zacc, key0 + 32, last_key);
       } else {
@@ -815,7 +821,7 @@ window_score_half_kernel(const __grid_constant__ CUtensorMap tmap_k, const Param
         float z = 0.f;
 #pragma unroll
         for (int g = 0; g < kParts; ++g) { const float2 a = xstat[g * 128 + et]; z += a.y * fast_exp2((a.x - mx) * kLog2e); }
-        crow[et] = (et / W < p.groups) ? (-mx * kLog2e - log2f(z)) : -INFINITY;
+        crow[et] = (et / W < gl) ? (-mx * kLog2e - log2f(z)) : -INFINITY;
       }
     }
     hepi_sync();
@@ -826,7 +832,7 @@ window_score_half_kernel(const __grid_constant__ CUtensorMap tmap_k, const Param
       const int key = tile_of(j) * kTile + r_loc;
       mbar_wait(tfull(buf), (j / kHNumBuf) & 1);
       tc_fence_after();
-      if ((wg * kCols) / W >= p.groups) {  // all chunks of this warpgroup lie beyond the last head
+      if ((wg * kCols) / W >= gl) {  // all chunks of this warpgroup lie beyond the last head
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty(buf));
         continue;
@@ -841,7 +847,7 @@ window_score_half_kernel(const __grid_constant__ CUtensorMap tmap_k, const Param
 #pragma unroll
       for (int c = 0; c < kChunks; ++c) {
         const int col0 = wg * kCols + c * 32;
-        if (col0 / W >= p.groups) continue;
+        if (col0 / W >= gl) continue;
         float2 acc[kHeadsPerChunk];
 #pragma unroll
         for (int h = 0; h < kHeadsPerChunk; ++h) acc[h] = make_float2(0.f, 0.f);
@@ -851,10 +857,10 @@ window_score_half_kernel(const __grid_constant__ CUtensorMap tmap_k, const Param
 #pragma unroll
           for (int h = 0; h < kHeadsPerChunk; ++h) {
             const int head = col0 / W + h;
-            if (head < p.groups) {
+            if (head < gl) {
               float sum = acc[h].x + acc[h].y;
               if (p.reduce_mean) sum = div_exact(sum, (float)p.w, 1.0f / (float)p.w);
-              p.out[((int64_t)b * p.Hq + kvh * p.groups + head) * nscore + key] = T::round1(sum);
+              p.out[((int64_t)b * p.Hq + kvh * p.groups + head0 + head) * nscore + key] = T::round1(sum);
             }
           }
         }
@@ -888,7 +894,7 @@ static int half_slot(cudaStream_t stream) {
 }
 
 template <typename T, int W, int NWG>
-static int launch_half(const CUtensorMap& tmap, const Params& sp, int units, cudaStream_t stream) {
+static int launch_half(const CUtensorMap& tmap, const Params& sp, int units, bool coop, cudaStream_t stream) {
   auto kern = window_score_half_kernel<T, W, NWG>;
   const int smem = HalfSmem::kAlloc;
   KVC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -901,27 +907,33 @@ static int launch_half(const CUtensorMap& tmap, const Params& sp, int units, cud
   cfg.stream = stream;
   // no programmatic dependent launch here: with two launches in flight a pre-launched successor of the same
   // stream competes with the other stream's launch for the free CTA slot of each SM (measured: 1.49 vs 1.46 ms)
+  // coop (KVC_IMPL_AUTO on shapes with several row blocks per KV head): cooperative launch, co-residency of the
+  // grid guaranteed by the driver whatever else the caller has in flight
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  if (coop) { cfg.attrs = attr; cfg.numAttrs = 1; }
   KVC_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, tmap, sp, slot));
   return launch_status("window_score_half_kernel");
 }
 
 template <typename T>
-static int dispatch_half(const CUtensorMap& tmap, const Params& sp, int units, cudaStream_t stream) {
+static int dispatch_half(const CUtensorMap& tmap, const Params& sp, int units, bool coop, cudaStream_t stream) {
   // four warpgroups (56 registers, 8 epilogue warps per SM sub-partition with two CTAs on the SM) measured 29.0 vs
   // 29.9 us per launch with two launches in flight, 1.431 vs 1.452 ms per cfg-2 step; KVC_HALF_WG=2 selects the
   // two-warpgroup build
   static const bool four = [] { const char* e = getenv("KVC_HALF_WG"); return !(e && atoi(e) == 2); }();
   if (four) {
     switch (sp.w) {
-      case 8: return launch_half<T, 8, 4>(tmap, sp, units, stream);
-      case 16: return launch_half<T, 16, 4>(tmap, sp, units, stream);
-      default: return launch_half<T, 32, 4>(tmap, sp, units, stream);
+      case 8: return launch_half<T, 8, 4>(tmap, sp, units, coop, stream);
+      case 16: return launch_half<T, 16, 4>(tmap, sp, units, coop, stream);
+      default: return launch_half<T, 32, 4>(tmap, sp, units, coop, stream);
     }
   }
   switch (sp.w) {
-    case 8: return launch_half<T, 8, 2>(tmap, sp, units, stream);
-    case 16: return launch_half<T, 16, 2>(tmap, sp, units, stream);
-    default: return launch_half<T, 32, 2>(tmap, sp, units, stream);
+    case 8: return launch_half<T, 8, 2>(tmap, sp, units, coop, stream);
+    case 16: return launch_half<T, 16, 2>(tmap, sp, units, coop, stream);
+    default: return launch_half<T, 32, 2>(tmap, sp, units, coop, stream);
   }
 }
 
@@ -930,17 +942,17 @@ struct Plan {
   size_t stats_bytes;
 };
 
-static Plan make_plan(int B, int Hq, int Hkv, int L, int w) {
+static Plan make_plan(int B, int Hq, int Hkv, int L, int w, bool split_rb = false) {
   Plan pl{};
   const int g = Hq / Hkv;
   pl.rb = (g * w + 127) / 128;
-  const int units = B * Hkv;
+  const int units = B * Hkv * (split_rb ? pl.rb : 1);   // the half-footprint kernel takes every row block as a unit
   const int tiles = (L + kTile - 1) / kTile;
   int cu = sm_count() / units;
   if (cu < 1) cu = 1;
   pl.chunk_tiles = (tiles + cu - 1) / cu;
   pl.nchunks = (tiles + pl.chunk_tiles - 1) / pl.chunk_tiles;
-  pl.stats_bytes = ((size_t)units * pl.nchunks * pl.rb * 128 * sizeof(float2) + 255) & ~(size_t)255;
+  pl.stats_bytes = ((size_t)units * pl.nchunks * (split_rb ? 1 : pl.rb) * 128 * sizeof(float2) + 255) & ~(size_t)255;
   return pl;
 }
 
@@ -1018,14 +1030,24 @@ bool window_scores_fused_supported(int B, int Hq, int Hkv, int L, int d, int w) 
   return B * Hkv * pl.nchunks <= sm_count();
 }
 
+// Shapes with several 128-row blocks per KV head (70B: 8 query heads x 32 window rows): the half-footprint kernel with
+// one unit per row block is faster than the two-accumulator full-size kernel (37.7 vs 41.0 us for one KV head at
+// 128K) -- KVC_IMPL_AUTO takes it when its grid fits.
+bool window_scores_split_preferred(int B, int Hq, int Hkv, int L, int d, int w) {
+  if (!window_scores_fused_supported(B, Hq, Hkv, L, d, w) || 128 % w) return false;
+  const tcf::Plan pl = tcf::make_plan(B, Hq, Hkv, L, w, true);
+  return pl.rb >= 2 && B * Hkv * pl.rb * pl.nchunks <= sm_count();
+}
+
 size_t window_scores_fused_workspace_bytes(int B, int Hq, int Hkv, int L, int d, int w) {
   if (!window_scores_tc_supported(B, Hq, Hkv, L, d, w)) return 0;
-  return tcf::make_plan(B, Hq, Hkv, L, w).stats_bytes + 256;
+  const size_t a = tcf::make_plan(B, Hq, Hkv, L, w).stats_bytes, b = tcf::make_plan(B, Hq, Hkv, L, w, true).stats_bytes;
+  return (a > b ? a : b) + 256;
 }
 
 int window_scores_fused(const void* q, int64_t q_sb, int64_t q_sh, int64_t q_sl, const void* k, int64_t k_sb,
                         int64_t k_sh, int64_t k_sl, int B, int Hq, int Hkv, int L, int d, int w, int dtype, int reduce,
-                        void* out_scores, void* workspace, size_t workspace_bytes, bool half, cudaStream_t stream) {
+                        void* out_scores, void* workspace, size_t workspace_bytes, int half, cudaStream_t stream) {
   using namespace tcf;
   KVC_REQUIRE(window_scores_fused_supported(B, Hq, Hkv, L, d, w), KVC_ERR_UNSUPPORTED,
               "fused tcgen05 scoring kernel does not cover this shape (Hq/Hkv=%d, w=%d, d=%d, units=%d)", Hq / Hkv, w, d,
@@ -1034,7 +1056,9 @@ int window_scores_fused(const void* q, int64_t q_sb, int64_t q_sh, int64_t q_sl,
               "tcgen05 scoring kernel: query rows must be 16-byte aligned");
   KVC_REQUIRE(((k_sb | k_sh | k_sl) & 7) == 0 && (reinterpret_cast<uintptr_t>(k) & 15) == 0, KVC_ERR_UNSUPPORTED,
               "tcgen05 scoring kernel: key rows must be 16-byte aligned (TMA)");
-  const Plan pl = make_plan(B, Hq, Hkv, L, w);
+  // half: 0 = full-size kernel, 1 = half-footprint kernel (plain launch: the caller keeps at most two in flight),
+  // 2 = half-footprint kernel launched cooperatively
+  const Plan pl = make_plan(B, Hq, Hkv, L, w, half != 0);
   KVC_REQUIRE(workspace_bytes >= pl.stats_bytes + 256, KVC_ERR_WORKSPACE, "window_scores workspace: have %zu need %zu",
               workspace_bytes, pl.stats_bytes + 256);
   EncodeTiledFn enc = encode_fn();
@@ -1062,8 +1086,13 @@ int window_scores_fused(const void* q, int64_t q_sb, int64_t q_sh, int64_t q_sl,
   sp.tl = KVC_TL_SLOT(0);
   const int units = B * Hkv;
   if (half) {
-    KVC_REQUIRE(pl.rb == 1, KVC_ERR_UNSUPPORTED, "half-footprint tcgen05 scoring kernel does not cover this shape: (Hq/Hkv)*w = %d > 128", (Hq / Hkv) * w);
-    return dtype == KVC_BF16 ? dispatch_half<Bf16>(tmap, sp, units, stream) : dispatch_half<Fp16>(tmap, sp, units, stream);
+    KVC_REQUIRE(128 % w == 0, KVC_ERR_UNSUPPORTED, "half-footprint tcgen05 scoring kernel: window %d does not divide 128", w);
+    KVC_REQUIRE(units * pl.rb * pl.nchunks <= sm_count(), KVC_ERR_UNSUPPORTED,
+                "half-footprint tcgen05 scoring kernel: %d CTAs exceed the %d SMs (two launches must be co-resident)",
+                units * pl.rb * pl.nchunks, sm_count());
+    sp.rbs = pl.rb;
+    return dtype == KVC_BF16 ? dispatch_half<Bf16>(tmap, sp, units * pl.rb, half == 2, stream)
+                             : dispatch_half<Fp16>(tmap, sp, units * pl.rb, half == 2, stream);
   }
   if (dtype == KVC_BF16)
     return pl.rb == 1 ? dispatch_w<Bf16, 1>(tmap, sp, units, stream) : dispatch_w<Bf16, 2>(tmap, sp, units, stream);

@@ -220,8 +220,7 @@ class _ScoredCluster:
         if scorer == "window":
             if pooling not in ("avgpool", "maxpool"):
                 raise ValueError("Pooling method not supported")
-            if self.async_tail and self.async_scores and (Hq // key_states.shape[1]) * w <= 128 and w <= 32 \
-                    and key_states.shape[-1] == 128 and window_lse is None:
+            if self.async_tail and self.async_scores and w <= 32 and key_states.shape[-1] == 128 and window_lse is None:
                 # fully asynchronous: the scoring goes to one of two rotating streams as the half-footprint
                 # kernel, so that the scoring launches of consecutive calls share every SM and fill each
                 # other's prologue / grid-barrier / tail gaps (29.4 vs 34.6 us per cfg-2 layer)
