@@ -615,7 +615,7 @@ def run_ours(args, wl):
     # DRAM traffic per launch of the dominant kernel from the committed ncu --set full capture
     traffic = None
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1c_traffic.json")))
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r2b_traffic.json")))
         kname = {"scores": "window_score_half_kernel" if use_half else "window_score_fused_kernel",
                  "select": "topk_cluster_kernel", "gather": "gather_rows_kernel"}
         if args.workload == "pyramidkv_llama3_8b_32k":
