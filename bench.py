@@ -20,6 +20,8 @@ Legs printed in ONE JSON line (rank 0):
   cfg5         BASELINE configs[4] as north_star states it: ONE Llama-3-70B prefill of 131 072 tokens, its 8 KV heads
                sharded 8/N per rank, 80 layers, HBM-cold inputs: strong scaling, no data-path collective
   cfg4         (N=1) BASELINE configs[3]: AdaKV at 64K, one layer's update_kv and the decode-side append
+  cfg1, cfg3   (N=1) BASELINE configs[0] (SnapKV, one layer at 4K) and configs[2] (H2O / StreamingLLM, Mistral-7B shapes,
+               32K, batch 8, one layer each)
   checks       (N>1) ShardedAdaKV's budget exchange over NCCL gives the single-GPU capacities
 ``--impl reference`` times the reference's CPU path alone on the same workload (bounded sample per step).
 
@@ -378,6 +380,74 @@ def measure_cfg4(torch, dev, peak_gbs):
     return out
 
 
+def _event_us(torch, fn, iters, warm):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record(); torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b) * 1e3)
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def measure_cfg1(torch, dev, peak_gbs):
+    """BASELINE configs[0]: SnapKV update_kv on one Llama-3-8B layer at L = 4096 (cap 128, avgpool 7): the drop-in call,
+    eager (one library call, three launches) and replayed from a CUDA graph over 6 rotating K/V sets."""
+    from kvcache_factory_b200 import SnapKVCluster
+    B, Hq, Hkv, L, d, w, cap = 1, 32, 8, 4096, 128, 32, 128
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(11)
+    r = lambda *sh: torch.randn(*sh, generator=gen, device=dev, dtype=torch.float32).to(torch.bfloat16)
+    Ks, Vs = [r(B, Hkv, L, d) for _ in range(6)], [r(B, Hkv, L, d) for _ in range(6)]
+    Q = r(B, Hq, L, d)
+    cl = SnapKVCluster(w, cap, 7, "avgpool")
+    turn = [0]
+
+    def call():
+        i = turn[0] = (turn[0] + 1) % 6
+        return cl.update_kv(Ks[i], Q, Vs[i], None, Hq // Hkv)
+
+    eager = _event_us(torch, call, 30, 5)
+    g, keep = _graph_of(torch, lambda: [call() for _ in range(12)])
+    rep = _time_replays(torch, g, 10) * 1e3 / 12
+    del keep
+    alg = B * Hkv * L * d * 2 + B * Hq * w * d * 2 + 4 * B * Hq * cap * d * 2
+    return {"workload": "snapkv_llama3_8b_4k_one_layer", "eager_us_per_layer": eager, "graph_us_per_layer": rep,
+            "alg_bytes": alg, "graph_hbm_frac": alg / (rep * 1e-6) / 1e9 / peak_gbs,
+            "note": "12.8 MB per layer: the three launches are latency-, not bandwidth-bound; inputs rotate over 6 sets "
+                    "(101 MB) but still fit the 126 MB L2"}
+
+
+def measure_cfg3(torch, dev, peak_gbs, peak_tf):
+    """BASELINE configs[2]: H2O and StreamingLLM on Mistral-7B shapes (32 q / 8 kv heads), L = 32768, budget 1024,
+    batch 8: one layer's update_kv each."""
+    from kvcache_factory_b200 import H2OKVCluster, StreamingLLMKVCluster
+    B, Hq, Hkv, L, d, w, cap = 8, 32, 8, 32768, 128, 32, 1024
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(12)
+    r = lambda *sh: torch.randn(*sh, generator=gen, device=dev, dtype=torch.float32).to(torch.bfloat16)
+    K, V, Q = r(B, Hkv, L, d), r(B, Hkv, L, d), r(B, Hq, L, d)
+    st = StreamingLLMKVCluster(w, cap, 7, "avgpool")
+    s_us = _event_us(torch, lambda: st.update_kv(K, Q, V, None, Hq // Hkv), 10, 3)
+    s_alg = 4 * B * Hq * cap * d * 2
+    h2o = H2OKVCluster(w, cap, 7, "avgpool")
+    h_us = _event_us(torch, lambda: h2o.update_kv(K, Q, V, None, Hq // Hkv), 2, 1)
+    flops = 4.0 * B * Hq * L * L * d          # two passes of Q.K^T over all L x L logits per head
+    out = {"workload": "h2o_streamingllm_mistral7b_32k_b8_one_layer",
+           "streamingllm_us_per_layer": s_us, "streamingllm_hbm_frac": s_alg / (s_us * 1e-6) / 1e9 / peak_gbs,
+           "h2o_ms_per_layer": h_us * 1e-3, "h2o_tflops": flops / (h_us * 1e-6) / 1e12,
+           "h2o_exps_per_s": 2.0 * B * Hq * L * L / (h_us * 1e-6),
+           "note": "H2O scores all L x L logits in two tcgen05 passes without materialising them: bound by the SFU "
+                   "(one exp per logit and pass, 16 per clock and SM = 4.65e12/s at 1965 MHz), not by the tensor pipe"}
+    if peak_tf:
+        out["h2o_tensor_frac"] = out["h2o_tflops"] / peak_tf
+    out["h2o_sfu_frac"] = out["h2o_exps_per_s"] / (16 * 148 * 1.965e9)
+    return out
+
+
 def check_sharded_adakv(torch, dist, dev, rank, world):
     """AdaKV's one exchange step on real NCCL: every rank runs ShardedAdaKV on its KV-head shard of the same seeded
     input; the capacities must equal those of the single-GPU AdaKVCluster over all heads (computed by every rank)."""
@@ -608,6 +678,7 @@ def run_ours(args, wl):
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_tf = float(peaks.get("bf16_tflops_sustained", 0.0)) or None   # H2O runs for ~0.2 s per layer: the sustained figure
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     dom_bytes_per_launch = alg[dominant] / nl if dominant != "select" else (sb + gb) / nl
     dom_ms = tot[dominant] / nl
@@ -661,12 +732,15 @@ def run_ours(args, wl):
     if graph is not None:
         del graph, graph_out
     torch.cuda.empty_cache()
-    cfg5 = cfg4 = checks = None
+    cfg5 = cfg4 = cfg1 = cfg3 = checks = None
     if not args.no_extra and args.workload == "pyramidkv_llama3_8b_32k":
         cfg5 = measure_cfg5(torch, dist if world > 1 else None, dev, rank, world, args.steps, not args.sync_tail,
                             not args.sync_tail and not args.sync_scores, peak)
         if world == 1:
             cfg4 = measure_cfg4(torch, dev, peak)
+            cfg1 = measure_cfg1(torch, dev, peak)
+            torch.cuda.empty_cache()
+            cfg3 = measure_cfg3(torch, dev, peak, peak_tf)
         else:
             checks = check_sharded_adakv(torch, dist, dev, rank, world)
 
@@ -692,7 +766,7 @@ def run_ours(args, wl):
                                    "hooks); sync_ms_per_step = the drop-in defaults"},
             "sync_ms_per_step": sync_ms,
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-            "cfg5": cfg5, "cfg4": cfg4, "checks": checks,
+            "cfg5": cfg5, "cfg4": cfg4, "cfg1": cfg1, "cfg3": cfg3, "checks": checks,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
