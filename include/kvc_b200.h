@@ -242,6 +242,22 @@ int kvc_adakv_hist_fine(const void* akeys, const int32_t* hist1, int H, int n, c
                         int32_t* out_hist2, int32_t* out_above, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * ThinK query-driven key-channel pruning of the compressed keys — replaces key_pruner_query_driven
+ * pyramidkv/pyramidkv_utils.py:13-26 (called from SnapKVCluster.update_think :349-392).
+ *
+ * k_compressed: contiguous [B,H,rows,d] (what update_kv returned); q: [B,H,L,d] with element strides, the last
+ * min(32, L) rows are read (:17).  The n_drop = int(d*ratio) channels with the smallest
+ * mean(q^2) * mean(k^2) (every step rounded to the model dtype) are removed from rows [0, rows-recent):
+ * out_pruned contiguous [B*H, rows-recent, d-n_drop], kept channels in channel order; out_mask uint8 [B,H,d],
+ * 1 = kept (the reference's ~mask).  The last `recent` rows stay as they are (a slice of k_compressed).
+ * ---------------------------------------------------------------------------------------------- */
+size_t kvc_think_prune_workspace_bytes(int B, int H, int rows, int d);
+int kvc_think_prune(const void* k_compressed, const void* q, int64_t q_sb, int64_t q_sh, int64_t q_sl,
+                    int B, int H, int L, int rows, int d, int recent, int n_drop, int dtype,
+                    void* out_pruned, uint8_t* out_mask, void* workspace, size_t workspace_bytes,
+                    void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Flattened-cache append — replaces tiny_api_cuda.update_flatten_view
  * csrc/csrc/cuda_api.cu:55-85 (kernel :11-53), called by DynamicCacheSplitHeadFlatten.update
  * pyramidkv/pyramidkv_utils.py:66-67.

@@ -19,6 +19,7 @@ from .pyramidkv_utils import (  # noqa: F401
     init_adakv,
     init_headkv,
     init_l2norm,
+    init_think,
     init_H2O,
     init_pyramidkv,
     init_snapkv,
@@ -29,7 +30,7 @@ from .pyramidkv_utils import (  # noqa: F401
 )
 
 __all__ = [
-    "AdaKVCluster", "DynamicCacheSplitHeadFlatten", "H2OKVCluster", "HeadKVCluster", "L2NormCluster", "init_headkv", "init_l2norm", "PyramidKVCluster", "SnapKVCluster",
+    "AdaKVCluster", "DynamicCacheSplitHeadFlatten", "H2OKVCluster", "HeadKVCluster", "L2NormCluster", "init_headkv", "init_l2norm", "init_think", "PyramidKVCluster", "SnapKVCluster",
     "StreamingLLMKVCluster", "init_adakv", "init_H2O", "init_pyramidkv", "init_snapkv", "init_StreamingLLM",
     "pyramid_budget", "repeat_kv", "wait_for_compression", "replace_llama", "replace_mistral",
 ]

@@ -62,6 +62,8 @@ _SIGNATURES = {
     "kvc_adakv_prefill": (c_int, [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _i, _i, _i, _i, _i, _i, _i, _i, _i,
                                   c_float, _i, _i, _i, _p, _p, _i64, _p, _p, _p, _p, _i, _p, c_size_t,
                                   POINTER(c_int), POINTER(c_int64), POINTER(c_size_t), _p]),
+    "kvc_think_prune_workspace_bytes": (c_size_t, [_i] * 4),
+    "kvc_think_prune": (c_int, [_p, _p, _i64, _i64, _i64, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, c_size_t, _p]),
     "kvc_update_flatten_view": (c_int, [_p, _p, _p, _p, _p, _i, _i, _i, _i64, _p]),
     "kvc_append_rows": (c_int, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p]),
     "kvc_flatten_regrow": (c_int, [_p, _p, _p, _p, _p, _i, _i, _i, _i64, _p]),
@@ -495,6 +497,29 @@ def adakv_hist_fine(akeys: torch.Tensor, hist1: torch.Tensor, thr_bin: torch.Ten
             akeys.data_ptr(), hist1.data_ptr(), H, n, thr_bin.data_ptr(), hist2.data_ptr(), above.data_ptr(),
             _stream(dev)))
     return hist2, above
+
+
+def think_prune(k_compressed: torch.Tensor, query_states: torch.Tensor, recent_size: int, ratio: float):
+    """ThinK channel pruning of the compressed keys (``key_pruner_query_driven``, pyramidkv_utils.py:13-26):
+    (kv_pruned [1, B*H, rows-recent, d-k], kv_recent [B,H,recent,d] (a view), mask bool [B,H,d], True = kept)."""
+    dev = _require_cuda(k_compressed, query_states)
+    B, H, rows, d = k_compressed.shape
+    if query_states.shape[0] != B or query_states.shape[1] != H or query_states.dtype != k_compressed.dtype:
+        raise ValueError("query_states must be [B,H,L,d] with the heads and dtype of the compressed keys")
+    L = query_states.shape[2]
+    kc = k_compressed.contiguous()
+    q = _rowmajor_last(query_states, 1)
+    n_drop = int(d * ratio)                                             # :15
+    recent = min(recent_size, rows)
+    pruned = torch.empty((1, B * H, rows - recent, d - n_drop), dtype=kc.dtype, device=dev)
+    mask = torch.empty((B, H, d), dtype=torch.bool, device=dev)
+    with torch.cuda.device(dev):
+        nbytes = max(256, lib().kvc_think_prune_workspace_bytes(B, H, rows, d))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        _check("kvc_think_prune", lib().kvc_think_prune(
+            kc.data_ptr(), q.data_ptr(), q.stride(0), q.stride(1), q.stride(2), B, H, L, rows, d, recent, n_drop,
+            dtype_code(kc.dtype), pruned.data_ptr(), mask.data_ptr(), ws.data_ptr(), nbytes, _stream(dev)))
+    return pruned, kc[:, :, rows - recent:, :], mask
 
 
 def update_flatten_view(cache: torch.Tensor, state: torch.Tensor, headlens: torch.Tensor,

@@ -42,6 +42,9 @@ int h2o_scores(const void*, int64_t, int64_t, int64_t, const void*, int64_t, int
                int, int, int, void*, void*, size_t, cudaStream_t);
 size_t adakv_allocate_workspace_bytes(int H, int n);
 int adakv_key_histogram(const void*, const float*, int, int, int, int, int32_t*, cudaStream_t);
+size_t think_prune_workspace_bytes(int BH, int rows, int d);
+int think_prune(const void*, const void*, int64_t, int64_t, int64_t, int, int, int, int, int, int, int, int, void*, uint8_t*, void*,
+                size_t, cudaStream_t);
 int adakv_hist_coarse(const void*, const float*, int, int, int, int, uint16_t*, int32_t*, cudaStream_t);
 int adakv_hist_fine(const uint16_t*, const int32_t*, int, int, const int32_t*, int32_t*, int32_t*, cudaStream_t);
 int adakv_allocate(const void*, const float*, int, int, int, int, float, int, int, int, int32_t*, int32_t*, int32_t*,
@@ -444,6 +447,23 @@ int kvc_adakv_key_histogram(const void* pooled, const float* sums, int H, int n,
   KVC_REQUIRE(H > 0 && n > 0, KVC_ERR_ARG, "H=%d n=%d", H, n);
   KVC_REQUIRE(dtype == KVC_BF16 || dtype == KVC_FP16, KVC_ERR_UNSUPPORTED, "dtype %d", dtype);
   return adakv_key_histogram(pooled, sums, H, n, dtype, normalize, out_hist, (cudaStream_t)stream);
+}
+
+size_t kvc_think_prune_workspace_bytes(int B, int H, int rows, int d) {
+  if (B <= 0 || H <= 0 || rows <= 0 || d <= 0) return 0;
+  return think_prune_workspace_bytes(B * H, rows, d);
+}
+
+int kvc_think_prune(const void* k_compressed, const void* q, int64_t q_sb, int64_t q_sh, int64_t q_sl, int B, int H, int L,
+                    int rows, int d, int recent, int n_drop, int dtype, void* out_pruned, uint8_t* out_mask, void* workspace,
+                    size_t workspace_bytes, void* stream) {
+  if (int rc = check_device()) return rc;
+  KVC_REQUIRE(k_compressed && q && out_mask && workspace && (out_pruned || rows <= recent || n_drop == d), KVC_ERR_ARG, "null pointer argument");
+  KVC_REQUIRE(B > 0 && H > 0 && L > 0 && rows > 0 && d > 0 && d <= 1024, KVC_ERR_ARG, "B=%d H=%d L=%d rows=%d d=%d", B, H, L, rows, d);
+  KVC_REQUIRE(recent >= 0 && n_drop >= 0 && n_drop <= d, KVC_ERR_ARG, "recent=%d n_drop=%d", recent, n_drop);
+  KVC_REQUIRE(dtype == KVC_BF16 || dtype == KVC_FP16, KVC_ERR_UNSUPPORTED, "dtype %d", dtype);
+  return think_prune(k_compressed, q, q_sb, q_sh, q_sl, B, H, L, rows, d, recent > rows ? rows : recent, n_drop, dtype, out_pruned,
+                     out_mask, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int kvc_update_flatten_view(void* dst, const void* src, const void* state, const int32_t* headlens,

@@ -307,6 +307,26 @@ class SnapKVCluster(_ScoredCluster):
                               window_lse=window_lse)
 
 
+    def update_think(self, key_states, query_states, value_states, attention_mask, num_key_value_groups):
+        """Reference ``update_think`` (``pyramidkv_utils.py:349-392``): the SnapKV compression, then ThinK's query-driven
+        pruning of ``int(d*ratio)`` key channels from all but the last ``recent_size`` compressed rows.  Returns
+        ``(kv_pruned, kv_recent, mask, value_states)``; ``(key_states, value_states)`` below the capacity (:357-358)."""
+        assert key_states.shape[-2] == query_states.shape[-2]
+        q_len = query_states.shape[-2]
+        _kv_heads(key_states, query_states, num_key_value_groups)
+        _trace(f"SnapKV max_capacity_prompt {self.max_capacity_prompt}")
+        if q_len < self.max_capacity_prompt:
+            return key_states, value_states
+        tail, self.async_tail = self.async_tail, False     # the pruner reads the gathered keys: same stream, in order
+        try:
+            kc, vc = self._compress(key_states, query_states, value_states,
+                                    self.max_capacity_prompt - self.window_size, scorer="window", pooling=self.pooling)
+        finally:
+            self.async_tail = tail
+        kv_pruned, kv_recent, mask = N.think_prune(kc, query_states, self.recent_size, self.ratio)
+        return kv_pruned, kv_recent, mask, vc
+
+
 class PyramidKVCluster(_ScoredCluster):
     """Reference ``PyramidKVCluster`` (``pyramidkv_utils.py:173-283``): per-layer pyramid budget."""
 
@@ -740,6 +760,19 @@ def init_StreamingLLM(self):
     self.kv_cluster = StreamingLLMKVCluster(
         window_size=self.config.window_size, max_capacity_prompt=self.config.max_capacity_prompt,
         kernel_size=self.config.kernel_size, pooling=self.config.pooling, merge=self.config.merge)
+    _apply_async_knobs(self.kv_cluster, self.config)
+
+
+def init_think(self):
+    """Reference ``init_think`` (``pyramidkv_utils.py:926-951``): a SnapKV cluster with ThinK's two knobs."""
+    if not hasattr(self, "kv_cluster"):
+        _defaults(self.config, window_size=32, max_capacity_prompt=4096, kernel_size=5, pooling='avgpool', merge=None,
+                  recent_size=32, ratio=0.4)
+    self.kv_cluster = SnapKVCluster(window_size=self.config.window_size,
+                                    max_capacity_prompt=self.config.max_capacity_prompt,
+                                    kernel_size=self.config.kernel_size, pooling=self.config.pooling,
+                                    merge=self.config.merge, recent_size=self.config.recent_size,
+                                    ratio=self.config.ratio)
     _apply_async_knobs(self.kv_cluster, self.config)
 
 

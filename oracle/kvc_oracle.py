@@ -154,6 +154,36 @@ def snapkv_update_kv(K, Q, V, window_size=64, max_capacity_prompt=320, kernel_si
     return _select(K, Q, V, window_size, max_capacity_prompt - window_size, kernel_size, pooling)
 
 
+def think_key_pruner(kv_states, q_states, recent_size=128, ratio=0.3):
+    """``key_pruner_query_driven`` (``pyramidkv_utils.py:13-26``): drop the ``int(d*ratio)`` key channels with the smallest
+    mean(q^2) * mean(k^2) from all but the last ``recent_size`` rows.  Returns (kv_pruned [1, B*H, rows-recent, d-k],
+    kv_recent, kept-channel mask [B,H,d], channel scores [B,H,d])."""
+    _, _, seqlen, head_dim = kv_states.shape
+    k = int(head_dim * ratio)
+    queries_norm = torch.pow(q_states[..., -32:, :], 2).mean(dim=2)      # the reference hard-codes 32 (:17)
+    keys_norm = torch.pow(kv_states, 2).mean(dim=2)
+    key = queries_norm * keys_norm
+    _, indices = torch.topk(key, k, dim=-1, largest=False)
+    keep_idx = indices.sort().values
+    mask = torch.zeros(key.shape, dtype=torch.bool)
+    mask = mask.scatter_(-1, keep_idx, 1)
+    mask_k = mask.unsqueeze(2).expand(-1, -1, seqlen - recent_size, -1)
+    pruned = kv_states[:, :, :seqlen - recent_size, :][~mask_k].reshape(1, -1, seqlen - recent_size, head_dim - k)
+    return pruned, kv_states[:, :, seqlen - recent_size:, :], ~mask, key
+
+
+def think_update_kv(K, Q, V, window_size=64, max_capacity_prompt=320, kernel_size=5, pooling="avgpool",
+                    recent_size=32, ratio=0.4):
+    """``SnapKVCluster.update_think`` (``pyramidkv_utils.py:349-392``): SnapKV compression, then channel pruning of the
+    compressed keys.  Returns (kv_pruned, kv_recent, mask, V', K', channel scores), or (K, V) on the pass-through
+    branch (``:357-358``)."""
+    Kc, Vc, idx, _ = snapkv_update_kv(K, Q, V, window_size, max_capacity_prompt, kernel_size, pooling)
+    if idx is None:
+        return Kc, Vc
+    pruned, recent, mask, key = think_key_pruner(Kc, Q, recent_size, ratio)
+    return pruned, recent, mask, Vc, Kc, key
+
+
 def pyramidkv_budget(q_len: int, window_size: int, max_capacity_prompt: int, num_hidden_layers: int,
                      layer_idx: int, beta: int = 20) -> int:
     """Per-layer number of non-window keys kept by PyramidKV (``pyramidkv_utils.py:205-215``)."""

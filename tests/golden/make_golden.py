@@ -74,6 +74,15 @@ CASES = {
                                knobs=dict(max_capacity_prompt=64, layer_idx=2, skip_layers=[])),
     "l2norm_skip":        dict(method="l2norm", B=1, Hq=4, Hkv=2, L=200, d=128, dtype="bf16", dist="normal",
                                knobs=dict(max_capacity_prompt=64, layer_idx=1, skip_layers=[0, 1])),
+    "think_bf16":         dict(method="think", B=1, Hq=8, Hkv=2, L=700, d=128, dtype="bf16", dist="peaked",
+                               knobs=dict(window_size=32, max_capacity_prompt=160, kernel_size=5, pooling="avgpool",
+                                          recent_size=32, ratio=0.4)),
+    "think_fp16":         dict(method="think", B=1, Hq=4, Hkv=4, L=500, d=128, dtype="fp16", dist="normal",
+                               knobs=dict(window_size=16, max_capacity_prompt=128, kernel_size=7, pooling="maxpool",
+                                          recent_size=16, ratio=0.25)),
+    "think_skip":         dict(method="think", B=1, Hq=4, Hkv=2, L=100, d=128, dtype="bf16", dist="normal",
+                               knobs=dict(window_size=32, max_capacity_prompt=160, kernel_size=5, pooling="avgpool",
+                                          recent_size=32, ratio=0.4)),
     "adakv_nocompress":   dict(method="adakv", B=1, Hq=4, Hkv=2, L=96, d=128, dtype="bf16", dist="normal",
                                knobs=dict(window_size=32, kernel_size=7, pooling="maxpool", max_capacity_prompt=128,
                                           floor=0.2, normalize=True)),
@@ -138,6 +147,19 @@ def run_case(ref, name: str, c: dict) -> dict:
         elif m == "streamingllm":
             cl = ref.StreamingLLMKVCluster(**kn)
             Kc, Vc = cl.update_kv(Kr, Q, Vr, None, shape.groups)
+        elif m == "think":
+            cl = ref.SnapKVCluster(**kn)
+            res = cl.update_think(Kr, Q, Vr, None, shape.groups)
+            if len(res) == 2:                                         # below the capacity: pass-through (:357-358)
+                Kc, Vc = res
+            else:
+                pruned, recent, mask, Vc = res
+                out["think_pruned"] = bits(pruned)
+                out["think_recent"] = bits(recent)
+                out["think_mask"] = mask.numpy()
+                # K' itself is not returned by update_think: the same cluster's update_kv gives it
+                Kc, _ = ref.SnapKVCluster(**kn).update_kv(Kr, Q, Vr, None, shape.groups)
+                out["think_key"] = bits(calls[1][0])                  # the channel scores topk(largest=False) ranks
         elif m == "l2norm":
             cl = ref.L2NormCluster(**kn)
             Kc, Vc = cl.update_kv(Kr, Q, Vr, None, shape.groups)
@@ -154,7 +176,7 @@ def run_case(ref, name: str, c: dict) -> dict:
             raise ValueError(m)
     out["K_out"] = bits(Kc)
     out["V_out"] = bits(Vc)
-    if m in ("snapkv", "pyramidkv", "h2o") and calls:
+    if m in ("snapkv", "pyramidkv", "h2o", "think") and calls:
         pooled, idx = calls[0]
         out["pooled"] = bits(pooled)
         out["idx"] = idx.numpy().astype(np.int64)

@@ -782,3 +782,63 @@ def test_window_scores_from_flash_attention_lse():
     agree = np.mean([len(set(ia[0, h].tolist()) & set(ib[0, h].tolist())) / (cap - w) for h in range(32)])
     assert agree >= 0.97, agree
     assert Kb.shape == Ka.shape and torch.equal(Kb[:, :, -w:], Ka[:, :, -w:])
+
+
+# ------------------------------------------------------------------------------------------------
+# f4: ThinK (SnapKV compression + query-driven key-channel pruning of the compressed keys)
+# ------------------------------------------------------------------------------------------------
+def _check_think(cl, Kd, Qd, Vd, g, d, dtype):
+    res = cl.update_think(Kd, Qd, Vd, None, g)
+    Kc, Vc = cl.update_kv(Kd, Qd, Vd, None, g)                      # the compressed cache the pruner saw (deterministic)
+    torch.cuda.synchronize()
+    pruned, recent, mask, Vt = res
+    rows, rs, k = Kc.shape[2], min(cl.recent_size, Kc.shape[2]), int(d * cl.ratio)
+    assert torch.equal(Vt, Vc) and torch.equal(recent, Kc[:, :, rows - rs:, :])
+    assert mask.dtype == torch.bool and tuple(mask.shape) == (Kc.shape[0], Kc.shape[1], d)
+    assert bool((mask.sum(-1) == d - k).all())
+    # the reference pruner on the same compressed keys (CPU restatement): channel scores differ from the kernel's only in
+    # the fp32 summation order -> every channel clearly below / above the k-th smallest score is dropped / kept
+    _, _, mask_ref, key = O.think_key_pruner(Kc.cpu(), Qd.cpu(), cl.recent_size, cl.ratio)
+    keyf = key.float()
+    kth = keyf.sort(-1).values[..., k - 1:k] if k > 0 else None
+    m = mask.cpu()
+    if k > 0:
+        tol = 4 * ulp_of(dtype)
+        assert not bool((m & (keyf < kth * (1 - tol))).any()), "a channel clearly below the threshold was kept"
+        assert not bool((~m & (keyf > kth * (1 + tol))).any()), "a channel clearly above the threshold was dropped"
+        assert float((m == mask_ref).float().mean()) > 0.97
+    # given the mask: kept channels in channel order, bit for bit (:26)
+    mk = m.unsqueeze(2).expand(-1, -1, rows - rs, -1)
+    want = Kc.cpu()[:, :, :rows - rs, :][mk].reshape(1, -1, rows - rs, d - k)
+    assert tuple(pruned.shape) == tuple(want.shape) and torch.equal(pruned.cpu(), want)
+    return mask, Kc
+
+
+@pytest.mark.parametrize("name", golden_cases("think"))
+def test_think_matches_reference_vectors(name):
+    c, z, (Q, K, V) = load_golden(name)
+    dtype = DTYPES[c["dtype"]]
+    g = c["Hq"] // c["Hkv"]
+    cl = SnapKVCluster(**c["knobs"])
+    Kd, Qd, Vd = K.to(dev()), Q.to(dev()), V.to(dev())
+    if name == "think_skip":
+        res = cl.update_think(Kd, Qd, Vd, None, g)
+        assert len(res) == 2 and res[0] is Kd and res[1] is Vd        # pass-through below the capacity (:357-358)
+        return
+    mask, Kc = _check_think(cl, Kd, Qd, Vd, g, c["d"], dtype)
+    if np.array_equal(to_bits(Kc.cpu()), z["K_out"]):                 # same compressed keys as the reference's run
+        key = from_bits(z["think_key"], dtype).float()
+        k = int(c["d"] * c["knobs"]["ratio"])
+        kth = key.sort(-1).values[..., k - 1:k]
+        m, mref = mask.cpu(), torch.from_numpy(z["think_mask"])
+        near = (key - kth).abs() <= 4 * ulp_of(dtype) * kth.abs()
+        assert bool(((m == mref) | near).all())
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_think_larger_shape_and_hf_layout(dtype):
+    shape = Shape(2, 8, 2, 2500, 128)
+    Q, K, V = make_qkv(shape, dtype, layer_idx=1, dist="peaked", window=32)
+    Qd = Q.to(dev()).transpose(1, 2).contiguous().transpose(1, 2)     # HF hands a transposed view
+    cl = SnapKVCluster(32, 512, 7, "maxpool", recent_size=48, ratio=0.3)
+    _check_think(cl, K.to(dev()), Qd, V.to(dev()), 4, 128, dtype)

@@ -54,6 +54,21 @@ def test_l2norm_matches_reference_vectors(name):
         assert np.array_equal(to_bits(norms), z["norms"])
 
 
+@pytest.mark.parametrize("name", golden_cases("think"))
+def test_think_matches_reference_vectors(name):
+    c, z, (Q, K, V) = load_golden(name)
+    res = O.think_update_kv(K, Q, V, **c["knobs"])
+    if name == "think_skip":
+        assert len(res) == 2 and np.array_equal(to_bits(res[0]), z["K_out"]) and np.array_equal(to_bits(res[1]), z["V_out"])
+        return
+    pruned, recent, mask, Vc, Kc, key = res
+    assert np.array_equal(to_bits(Kc), z["K_out"]) and np.array_equal(to_bits(Vc), z["V_out"])
+    assert np.array_equal(to_bits(key), z["think_key"])
+    assert np.array_equal(mask.numpy(), z["think_mask"])
+    assert tuple(pruned.shape) == tuple(z["think_pruned"].shape)
+    assert np.array_equal(to_bits(pruned), z["think_pruned"]) and np.array_equal(to_bits(recent), z["think_recent"])
+
+
 @pytest.mark.parametrize("name", golden_cases("adakv"))
 def test_adakv_matches_reference_vectors(name):
     c, z, (Q, K, V) = load_golden(name)
