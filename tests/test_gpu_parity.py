@@ -265,6 +265,44 @@ def test_pool_topk_matches_torch(pooling, kernel, dtype, n, k):
     assert torch.allclose(sums[:, 1].cpu(), ref_pooled.float().sum(-1), rtol=1e-5)
 
 
+def _dist(name, rows, n, g):
+    if name == "ties":          # few distinct values: the threshold bin is one key with thousands of ties
+        return (torch.randint(0, 12, (rows, n), generator=g).float() / 8)
+    if name == "constant":      # key range 0
+        return torch.full((rows, n), 0.37)
+    if name == "concentrated":  # almost everything inside one adaptive bin: the one-round shortcut must fall back
+        return 1.0 + torch.rand(rows, n, generator=g) * 2e-2
+    if name == "zeros":         # underflowed probabilities: mostly exact zeros, a heavy tail
+        x = torch.rand(rows, n, generator=g) ** 16
+        return torch.where(x < 1e-3, torch.zeros(()), x)
+    if name == "negative":      # L2Norm scores are negated norms
+        return -(torch.rand(rows, n, generator=g) * 30 + 0.5)
+    return torch.rand(rows, n, generator=g) ** 8 * 4          # "heavy": softmax-like tail
+
+
+@pytest.mark.parametrize("dist", ["heavy", "ties", "constant", "concentrated", "zeros", "negative"])
+@pytest.mark.parametrize("n,k", [(32736, 2016), (32768, 4096), (32736, 4097), (16385, 1), (8193, 8192), (4097, 4097),
+                                 (65504, 3038), (131040, 172), (20000, 8192), (700, 128)])
+def test_pool_topk_index_only_paths(dist, n, k):
+    """Indices without sums: the path the clusters use (one counting round when the threshold bin fits the sort buffers,
+    compaction bases from the per-CTA histograms) on distributions that stress the binning."""
+    g = torch.Generator().manual_seed(n * 7 + k)
+    rows = 5
+    dtype = torch.bfloat16 if (n + k) % 2 == 0 else torch.float16
+    s = _dist(dist, rows, n, g).to(dtype)
+    for pooling, kernel in (("avgpool", 7), ("maxpool", 5), (None, 1)):
+        ref_pooled = O.pool_scores(s.view(1, rows, n), kernel, pooling).view(rows, n)
+        idx, _, _ = _native.pool_topk(s.to(dev()), kernel, pooling, k)
+        idx = idx.cpu().long()
+        assert int(idx.min()) >= 0 and int(idx.max()) < n
+        vals = ref_pooled.float().gather(1, idx)
+        assert torch.equal(vals, ref_pooled.float().topk(k, dim=-1).values), (dist, pooling, "values differ from torch.topk")
+        for r in range(rows):
+            assert idx[r].unique().numel() == k
+            same = vals[r][1:] == vals[r][:-1]
+            assert bool((idx[r][1:][same] > idx[r][:-1][same]).all()), "ties must be ordered by ascending position"
+
+
 def test_pool_topk_per_row_k():
     g = torch.Generator().manual_seed(5)
     rows, n = 8, 5000
