@@ -501,7 +501,7 @@ def run_ours(args, wl):
     B, Hq, Hkv, L, d, w, nl = wl["B"], wl["Hq"], wl["Hkv"], wl["L"], wl["d"], wl["window"], wl["layers"]
     dtype = torch.bfloat16 if wl["dtype"] == "bf16" else torch.float16
     impl = {"auto": _native.IMPL_AUTO, "mma": _native.IMPL_MMA_SYNC, "tc": _native.IMPL_TCGEN05,
-            "fused": _native.IMPL_TCGEN05_FUSED}[args.score_impl]
+            "fused": _native.IMPL_TCGEN05_FUSED, "half": _native.IMPL_TCGEN05_HALF, "dyn": _native.IMPL_TCGEN05_DYN}[args.score_impl]
 
     # synthetic inputs, device resident; each rank draws its own shard of the N-request batch
     g = torch.Generator(device=dev)
@@ -780,7 +780,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="pyramidkv_llama3_8b_32k", choices=sorted(WORKLOADS))
-    ap.add_argument("--score-impl", default="auto", choices=["auto", "mma", "tc", "fused"])
+    ap.add_argument("--score-impl", default="auto", choices=["auto", "mma", "tc", "fused", "half", "dyn"])
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
     ap.add_argument("--sync-tail", action="store_true", help="keep select+gather on the caller's stream")
     ap.add_argument("--sync-scores", action="store_true", help="keep the scoring kernel on the caller's stream")

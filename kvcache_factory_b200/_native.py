@@ -132,15 +132,46 @@ def _require_cuda(*tensors: torch.Tensor) -> torch.device:
     return dev
 
 
+class _on_device:
+    """``with torch.cuda.device(dev)`` only when ``dev`` is not the current device already: the guard costs ~5 us of host
+    time per call, which is what the eager drop-in path of short prompts is bound by."""
+    __slots__ = ("dev", "guard")
+
+    def __init__(self, dev: torch.device):
+        self.dev, self.guard = dev, None
+
+    def __enter__(self):
+        if self.dev.index is not None and torch.cuda.current_device() != self.dev.index:
+            self.guard = torch.cuda.device(self.dev)
+            self.guard.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.guard is not None:
+            return self.guard.__exit__(*exc)
+        return False
+
+
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream(dev: torch.device) -> int:
+    """Handle of the caller's current stream on ``dev`` (the raw getter is ~7 us cheaper than building a Stream object)."""
+    if _raw_stream is not None:
+        return _raw_stream(dev.index if dev.index is not None else torch.cuda.current_device())
     return torch.cuda.current_stream(dev).cuda_stream
 
 
 def _rowmajor_last(t: torch.Tensor, align_elems: int) -> torch.Tensor:
     """Kernels need a unit-stride last dim and (for K/V) 16-byte aligned rows; HF tensors have both.
     Anything else is repacked once on the device (a copy kernel, not a compute fallback)."""
-    ok = t.stride(-1) == 1 and all(s % align_elems == 0 for s in t.stride()[:-1]) \
-        and t.data_ptr() % (2 * align_elems) == 0
+    st = t.stride()
+    ok = st[-1] == 1 and t.data_ptr() % (2 * align_elems) == 0
+    if ok:
+        for s in st[:-1]:
+            if s % align_elems:
+                ok = False
+                break
     return t if ok else t.contiguous()
 
 
@@ -180,7 +211,7 @@ def window_scores(query_states: torch.Tensor, key_states: torch.Tensor, window_s
         q_ptr = q8.data_ptr()
         if Lq != L:
             q_ptr -= (L - window_size) * q8.stride(2) * q8.element_size()
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             ws_bytes = lib().kvc_window_scores_workspace_bytes(B, Hq, Hkv, L, d, window_size)
             ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=dev)
             _check("kvc_window_scores_lse", lib().kvc_window_scores_lse(
@@ -188,7 +219,7 @@ def window_scores(query_states: torch.Tensor, key_states: torch.Tensor, window_s
                 lse.data_ptr(), B, Hq, Hkv, L, d, window_size, code, REDUCE_MEAN if reduce == "mean" else REDUCE_SUM,
                 out.data_ptr(), ws.data_ptr(), ws.numel(), _stream(dev)))
         return out
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         ws_bytes = lib().kvc_window_scores_workspace_bytes(B, Hq, Hkv, L, d, window_size)
         ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=dev)
         _check("kvc_window_scores", lib().kvc_window_scores(
@@ -207,7 +238,7 @@ def h2o_scores(query_states: torch.Tensor, key_states: torch.Tensor, window_size
     q = _rowmajor_last(query_states, 8)
     k = _rowmajor_last(key_states, 8)
     out = torch.empty((B, Hq, L - window_size), dtype=key_states.dtype, device=dev)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         ws_bytes = lib().kvc_h2o_scores_workspace_bytes(B, Hq, Hkv, L, d, window_size)
         ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=dev)
         _check("kvc_h2o_scores", lib().kvc_h2o_scores(
@@ -248,7 +279,7 @@ def _pool_topk(scores, kernel_size, pooling, k, k_per_row, want_pooled, want_sum
         if k_per_row.dtype != torch.int32 or k_per_row.numel() != rows:
             raise TypeError("k_per_row must be an int32 tensor with one entry per row")
         _require_cuda(scores, k_per_row)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         ws_bytes = lib().kvc_pool_topk_workspace_bytes(rows, n, k)
         ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=dev)
         _check("kvc_pool_topk", lib().kvc_pool_topk(
@@ -289,7 +320,7 @@ def gather_dense(key_states: torch.Tensor, value_states: torch.Tensor, idx, num_
             raise TypeError("idx must be a contiguous int32 tensor")
     out_k = torch.empty((B, num_heads, n_sel + window_size, d), dtype=k.dtype, device=dev)
     out_v = torch.empty_like(out_k)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         _check("kvc_gather_dense", lib().kvc_gather_dense(
             k.data_ptr(), k.stride(0), k.stride(1), k.stride(2),
             v.data_ptr(), v.stride(0), v.stride(1), v.stride(2),
@@ -305,7 +336,7 @@ def key_norm_scores(key_states: torch.Tensor, num_heads: int) -> torch.Tensor:
     code = dtype_code(key_states.dtype)
     k = _rowmajor_last(key_states, 8)
     out = torch.empty((B, num_heads, L), dtype=key_states.dtype, device=dev)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         _check("kvc_key_norm_scores", lib().kvc_key_norm_scores(
             k.data_ptr(), k.stride(0), k.stride(1), k.stride(2), B, num_heads, Hkv, L, d, code, out.data_ptr(),
             _stream(dev)))
@@ -345,7 +376,7 @@ def compress_dense(query_states: torch.Tensor, key_states: torch.Tensor, value_s
     out_k = torch.empty((B, num_heads, n_keep + window_size, d), dtype=k.dtype, device=dev)
     out_v = torch.empty_like(out_k)
     key = (dev.index, B, num_heads, Hkv, L, d, window_size, n_keep)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         nbytes = _ws_bytes_cache.get(key)
         if nbytes is None:
             nbytes = _ws_bytes_cache[key] = max(256, lib().kvc_compress_dense_workspace_bytes(B, num_heads, Hkv, L, d, window_size, n_keep))
@@ -375,7 +406,7 @@ def gather_varlen(key_states, value_states, idx, cap, cu_klen, num_heads: int, w
     v = _rowmajor_last(value_states, 16 // e)
     out_k = torch.empty((total_rows, d), dtype=k.dtype, device=dev)
     out_v = torch.empty_like(out_k)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         _check("kvc_gather_varlen", lib().kvc_gather_varlen(
             k.data_ptr(), k.stride(1), k.stride(2), v.data_ptr(), v.stride(1), v.stride(2),
             idx.data_ptr(), idx.stride(-2), cap.data_ptr(), cu_klen.data_ptr(), num_heads, Hkv, L, d, window_size,
@@ -394,7 +425,7 @@ def adakv_allocate(pooled: torch.Tensor, sums: torch.Tensor, base_capacity: int,
     cu_klen = torch.empty(H + 1, dtype=torch.int32, device=dev)
     # torch evaluates `counts * (1 - floor_ratio)` with the Python double rounded to fp32
     one_minus_floor = float(torch.tensor(1 - floor_ratio, dtype=torch.float32))
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         ws_bytes = lib().kvc_adakv_allocate_workspace_bytes(H, n)
         ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=dev)
         _check("kvc_adakv_allocate", lib().kvc_adakv_allocate(
@@ -435,7 +466,7 @@ def adakv_prefill(query_states: torch.Tensor, key_states: torch.Tensor, value_st
         host = _pinned_caps[(dev.index, H)] = torch.empty(H, dtype=torch.int32).pin_memory()
     one_minus_floor = float(np.float32(1 - floor_ratio))                          # as torch evaluates it (:719)
     bound = n    # index rows and select scratch sized for the widest possible head: workspace bytes, not work
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         key = ("adakv", dev.index, H, Hkv, L, d, w, bound)
         nbytes = _ws_bytes_cache.get(key)
         if nbytes is None:
@@ -464,7 +495,7 @@ def adakv_key_histogram(pooled: torch.Tensor, sums: torch.Tensor, normalize: boo
     dev = _require_cuda(pooled, sums)
     H, n = pooled.shape
     hist = torch.empty((H, 65536), dtype=torch.int32, device=dev)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         _check("kvc_adakv_key_histogram", lib().kvc_adakv_key_histogram(
             pooled.contiguous().data_ptr(), sums.data_ptr(), H, n, dtype_code(pooled.dtype), int(bool(normalize)),
             hist.data_ptr(), _stream(dev)))
@@ -477,7 +508,7 @@ def adakv_hist_coarse(pooled: torch.Tensor, sums: torch.Tensor, normalize: bool)
     H, n = pooled.shape
     akeys = torch.empty((H, n), dtype=torch.int16, device=dev)
     hist1 = torch.empty((H, 4096), dtype=torch.int32, device=dev)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         _check("kvc_adakv_hist_coarse", lib().kvc_adakv_hist_coarse(
             pooled.contiguous().data_ptr(), sums.data_ptr(), H, n, dtype_code(pooled.dtype), int(bool(normalize)),
             akeys.data_ptr(), hist1.data_ptr(), _stream(dev)))
@@ -492,7 +523,7 @@ def adakv_hist_fine(akeys: torch.Tensor, hist1: torch.Tensor, thr_bin: torch.Ten
     H, n = akeys.shape
     hist2 = torch.empty((H, 16), dtype=torch.int32, device=dev)
     above = torch.empty(H, dtype=torch.int32, device=dev)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         _check("kvc_adakv_hist_fine", lib().kvc_adakv_hist_fine(
             akeys.data_ptr(), hist1.data_ptr(), H, n, thr_bin.data_ptr(), hist2.data_ptr(), above.data_ptr(),
             _stream(dev)))
@@ -513,7 +544,7 @@ def think_prune(k_compressed: torch.Tensor, query_states: torch.Tensor, recent_s
     recent = min(recent_size, rows)
     pruned = torch.empty((1, B * H, rows - recent, d - n_drop), dtype=kc.dtype, device=dev)
     mask = torch.empty((B, H, d), dtype=torch.bool, device=dev)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         nbytes = max(256, lib().kvc_think_prune_workspace_bytes(B, H, rows, d))
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         _check("kvc_think_prune", lib().kvc_think_prune(
@@ -538,7 +569,7 @@ def update_flatten_view(cache: torch.Tensor, state: torch.Tensor, headlens: torc
     cache = cache.contiguous()
     state = state.contiguous()
     out = torch.empty((total + H, d), dtype=cache.dtype, device=dev)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         _check("kvc_update_flatten_view", lib().kvc_update_flatten_view(
             out.data_ptr(), cache.data_ptr(), state.data_ptr(), headlens.data_ptr(), cu_headlens.data_ptr(),
             H, d, cache.element_size(), total, _stream(dev)))
@@ -555,7 +586,7 @@ def append_rows(k_buf: torch.Tensor, v_buf: torch.Tensor, new_k: torch.Tensor, n
     H, d = new_k.shape
     if not (k_buf.is_contiguous() and v_buf.is_contiguous()):
         raise RuntimeError("slack-layout cache buffers must be contiguous")
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         _check("kvc_append_rows", lib().kvc_append_rows(
             k_buf.data_ptr(), v_buf.data_ptr(), new_k.contiguous().data_ptr(), new_v.contiguous().data_ptr(),
             cu_cap.data_ptr(), head_lens.data_ptr(), H, d, k_buf.element_size(), _stream(dev)))
@@ -568,7 +599,7 @@ def flatten_regrow(src: torch.Tensor, head_lens: torch.Tensor, cu_src: torch.Ten
     dtype_code(src.dtype)
     H, d = head_lens.shape[0], src.shape[1]
     dst = torch.empty((total_dst_rows, d), dtype=src.dtype, device=dev)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         _check("kvc_flatten_regrow", lib().kvc_flatten_regrow(
             dst.data_ptr(), src.contiguous().data_ptr(), head_lens.data_ptr(), cu_src.data_ptr(), cu_dst.data_ptr(),
             H, d, src.element_size(), src.shape[0], _stream(dev)))

@@ -1,6 +1,7 @@
 // Shared device/host helpers for libkvc_b200 (sm_100a only).
 #pragma once
 
+#include <atomic>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -159,5 +160,19 @@ __device__ __forceinline__ float div_exact(float s, float d, float rcp) {
   const float r = fmaf(-q, d, a);
   return fmaf(r, rcp, q) * down;
 }
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (call site = kernel instance, device) and only when the
+// request grows: the call costs ~1 us of host time, which the eager drop-in path of short prompts is bound by.
+// The call-site statics live in function templates, i.e. one set per kernel instantiation.
+#define KVC_SET_MAX_SMEM(kern, bytes)                                                                          \
+  do {                                                                                                         \
+    static std::atomic<int> kvc_smem_set_[64];                                                                 \
+    int kvc_dev_ = 0;                                                                                          \
+    if (cudaGetDevice(&kvc_dev_) != cudaSuccess || kvc_dev_ < 0 || kvc_dev_ >= 64) kvc_dev_ = 0;               \
+    if (kvc_smem_set_[kvc_dev_].load(std::memory_order_relaxed) < (int)(bytes)) {                              \
+      KVC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));     \
+      kvc_smem_set_[kvc_dev_].store((int)(bytes), std::memory_order_relaxed);                                  \
+    }                                                                                                          \
+  } while (0)
 
 }  // namespace kvc

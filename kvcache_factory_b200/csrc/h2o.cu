@@ -417,8 +417,8 @@ template <typename T>
 static int launch(const CUtensorMap& mk, const CUtensorMap& mq, const Params& sp, cudaStream_t stream) {
   auto k1 = h2o_kernel<T, false>;
   auto k2 = h2o_kernel<T, true>;
-  KVC_CUDA_TRY(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::kAlloc));
-  KVC_CUDA_TRY(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::kAlloc));
+  KVC_SET_MAX_SMEM(k1, Smem::kAlloc);
+  KVC_SET_MAX_SMEM(k2, Smem::kAlloc);
   k1<<<dim3(sp.tiles, sp.B * sp.Hq), kThreads, Smem::kAlloc, stream>>>(mk, mq, sp);
   if (int rc = launch_status("h2o_kernel<stats>")) return rc;
   const int ktiles = (sp.L - sp.w + kTile - 1) / kTile;

@@ -554,7 +554,7 @@ static int launch(const CUtensorMap& tmap, const Params& sp, const Plan& pl, cud
   static const bool poly = [] { const char* e = getenv("KVC_DYN_POLY"); return !(e && e[0] == '0'); }();
   auto kern = poly ? window_score_dyn_kernel<T, W, 4, 4> : window_score_dyn_kernel<T, W, 0, 0>;
   const int smem = Smem::kAlloc;
-  KVC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  KVC_SET_MAX_SMEM(kern, smem);
   const int slot = ctl_slot(stream);
   KVC_REQUIRE(slot >= 0, KVC_ERR_UNSUPPORTED, "dynamic tcgen05 scoring kernel: more than %d distinct streams on this device", kSlots);
   Ctl* ctl = nullptr;

@@ -897,7 +897,7 @@ template <typename T, int W, int NWG>
 static int launch_half(const CUtensorMap& tmap, const Params& sp, int units, bool coop, cudaStream_t stream) {
   auto kern = window_score_half_kernel<T, W, NWG>;
   const int smem = HalfSmem::kAlloc;
-  KVC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  KVC_SET_MAX_SMEM(kern, smem);
   const int slot = half_slot(stream);
   KVC_REQUIRE(slot >= 0, KVC_ERR_UNSUPPORTED, "half-footprint tcgen05 scoring kernel: more than %d distinct streams on this device", kHSlots);
   cudaLaunchConfig_t cfg{};
@@ -975,7 +975,7 @@ template <typename T, int RB, int W>
 static int launch(const CUtensorMap& tmap, const Params& sp, int units, cudaStream_t stream) {
   auto kern = window_score_fused_kernel<T, RB, W>;
   const int smem = Smem<RB>::kAlloc;
-  KVC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  KVC_SET_MAX_SMEM(kern, smem);
   // cooperative launch: the grid is scheduled only when every CTA can be resident, so two grids
   // with barriers (other streams / processes) can never hold each other's SMs hostage
   cudaLaunchConfig_t cfg{};

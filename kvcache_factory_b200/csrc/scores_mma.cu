@@ -361,8 +361,8 @@ static int launch_both(const ScoreParams& sp, int units_blk, cudaStream_t stream
   const size_t smem = score_smem_bytes<D>(SLABS);
   auto k1 = window_score_mma_kernel<T, SLABS, D, false>;
   auto k2 = window_score_mma_kernel<T, SLABS, D, true>;
-  KVC_CUDA_TRY(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  KVC_CUDA_TRY(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  KVC_SET_MAX_SMEM(k1, (int)smem);
+  KVC_SET_MAX_SMEM(k2, (int)smem);
   dim3 grid(sp.nchunks, units_blk);
   k1<<<grid, Tiling<SLABS>::NT, smem, stream>>>(sp);
   if (int rc = launch_status("window_score_mma_kernel<stats>")) return rc;

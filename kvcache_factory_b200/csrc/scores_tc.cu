@@ -501,8 +501,8 @@ static int launch_pair(const CUtensorMap& tmap, const Params& sp, int units, cud
   auto k1 = window_score_tc_kernel<T, false, RB, W>;
   auto k2 = window_score_tc_kernel<T, true, RB, W>;
   const int smem = Smem<RB>::kAlloc;
-  KVC_CUDA_TRY(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  KVC_CUDA_TRY(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  KVC_SET_MAX_SMEM(k1, smem);
+  KVC_SET_MAX_SMEM(k2, smem);
   dim3 grid(sp.nchunks, units);
   k1<<<grid, kThreads, smem, stream>>>(tmap, sp);
   if (int rc = launch_status("window_score_tc_kernel<stats>")) return rc;

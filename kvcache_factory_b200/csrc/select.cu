@@ -276,7 +276,7 @@ int pool_topk(const void* scores, int rows, int n, int dtype, int kernel_size, i
   const int sort_smem_cap = kpad > kSortSmemMax ? kSortSmemMax : kpad;
   const size_t smem = sizeof(SelShared) + (size_t)sort_smem_cap * 8;
   auto kern = dtype == KVC_BF16 ? pool_topk_kernel<Bf16> : pool_topk_kernel<Fp16>;
-  KVC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (dtype == KVC_BF16) { KVC_SET_MAX_SMEM(pool_topk_kernel<Bf16>, (int)smem); } else { KVC_SET_MAX_SMEM(pool_topk_kernel<Fp16>, (int)smem); }
   kern<<<rows, kSelThreads, smem, stream>>>((const uint16_t*)scores, n, kernel_size, pool, k, k_per_row, out_idx,
                                             idx_stride, (uint16_t*)out_pooled, out_sums, keys, sort_scratch, kpad,
                                             sort_smem_cap);

@@ -553,7 +553,7 @@ static int launch(const void* scores, int rows, int n, int C, int kernel_size, i
   const size_t stage_bytes = (size_t)(kThreads * E + 2 * kHalo + 2 * (kThreads + 2)) * 2;
   const size_t sort_bytes = (size_t)(kThreads == 1024 ? kMaxK : kMaxK / 2) * 12;
   const size_t smem = ((sizeof(Shared) + 15) & ~(size_t)15) + (stage_bytes > sort_bytes ? stage_bytes : sort_bytes);
-  KVC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  KVC_SET_MAX_SMEM(kern, (int)smem);
   if (C > 8) KVC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(C, rows);
