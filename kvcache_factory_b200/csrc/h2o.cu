@@ -14,7 +14,10 @@
 // accumulator buffers).  This path is exp-throughput bound (2*L^2 exps per head), not HBM bound.
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
+#include "tc_helpers.cuh"
 
 namespace kvc {
 namespace h2o {
@@ -161,7 +164,7 @@ __device__ __forceinline__ void p1_chunk(const uint32_t (&v)[32], float scale, f
 }
 
 // Pass 2, one chunk of 32 query rows of this thread's key: p = exp2(x*log2e + c_row) rounded to dtype, summed in fp32.
-template <typename T>
+template <typename T, int POLY>
 __device__ __forceinline__ float p2_chunk(const uint32_t (&v)[32], float scale, const float4* __restrict__ cg) {
   const float2 scale2 = make_float2(scale, scale);
   const float2 l2e2 = make_float2(kLog2e, kLog2e);
@@ -174,13 +177,14 @@ __device__ __forceinline__ float p2_chunk(const uint32_t (&v)[32], float scale, 
       const int i = 2 * q4 + h;
       float2 f = __fmul2_rn(make_float2(T::rnd(__uint_as_float(v[2 * i])), T::rnd(__uint_as_float(v[2 * i + 1]))), scale2);
       f = __ffma2_rn(make_float2(T::rnd(f.x), T::rnd(f.y)), l2e2, h == 0 ? make_float2(c4.x, c4.y) : make_float2(c4.z, c4.w));
-      acc[h] = __fadd2_rn(acc[h], make_float2(T::rnd(fast_exp2(f.x)), T::rnd(fast_exp2(f.y))));
+      const float2 e = i < POLY ? tcx::exp2_fma2(f) : make_float2(fast_exp2(f.x), fast_exp2(f.y));   // FMA-pipe exp2 for POLY of 16 pairs
+      acc[h] = __fadd2_rn(acc[h], make_float2(T::rnd(e.x), T::rnd(e.y)));
     }
   }
   return (acc[0].x + acc[0].y) + (acc[1].x + acc[1].y);
 }
 
-template <typename T, bool kPass2>
+template <typename T, bool kPass2, int POLY>
 __global__ void __launch_bounds__(kThreads, 1)
 h2o_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_q, const Params p) {
   extern __shared__ unsigned char smem_raw[];
@@ -327,16 +331,16 @@ h2o_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ C
         const int row = blk * kTile + r_loc, key0 = j * kTile + wg * 32;
         if (key0 + 32 > nscore) {  // chunk touches the w x w causal block or runs past L
           const int last_key = min(p.L - 1, row >= nscore ? row : p.L - 1);
-          p1_chunk<T, true>(v, scale, m_run, zacc, key0, last_key);
+          tcx::p1_chunk<T, true, POLY>(v, scale, m_run, zacc, key0, last_key);
         } else {
-          p1_chunk<T, false>(v, scale, m_run, zacc, 0, 0);
+          tcx::p1_chunk<T, false, POLY>(v, scale, m_run, zacc, 0, 0);
         }
       } else {
         // thread <-> key blk*128 + r_loc; this warpgroup's columns are query rows 32*wg.. of (head hl, row block rbk)
         const float4* cg = reinterpret_cast<const float4*>(p.cbuf + ((int64_t)b * p.Hq + kvh * p.groups + hl) * (p.tiles * kTile) +
                                                             (int64_t)rbk * kTile + wg * 32);
         float* slot = aux + (wg * kMaxGroups + hl) * 128 + r_loc;  // only this thread touches this slot
-        *slot += p2_chunk<T>(v, scale, cg);
+        *slot += p2_chunk<T, POLY>(v, scale, cg);
         if (++hl == p.groups) { hl = 0; ++rbk; }
       }
     }
@@ -413,10 +417,10 @@ static int make_map(CUtensorMap* tmap, const void* ptr, int64_t sb, int64_t sh, 
   return 0;
 }
 
-template <typename T>
+template <typename T, int POLY>
 static int launch(const CUtensorMap& mk, const CUtensorMap& mq, const Params& sp, cudaStream_t stream) {
-  auto k1 = h2o_kernel<T, false>;
-  auto k2 = h2o_kernel<T, true>;
+  auto k1 = h2o_kernel<T, false, POLY>;
+  auto k2 = h2o_kernel<T, true, POLY>;
   KVC_SET_MAX_SMEM(k1, Smem::kAlloc);
   KVC_SET_MAX_SMEM(k2, Smem::kAlloc);
   k1<<<dim3(sp.tiles, sp.B * sp.Hq), kThreads, Smem::kAlloc, stream>>>(mk, mq, sp);
@@ -455,7 +459,12 @@ int h2o_scores(const void* q, int64_t q_sb, int64_t q_sh, int64_t q_sl, const vo
   sp.scale = 1.0f / sqrtf((float)d);
   sp.cbuf = (float*)workspace;
   sp.out = (uint16_t*)out_scores;
-  return dtype == KVC_BF16 ? launch<Bf16>(mk, mq, sp, stream) : launch<Fp16>(mk, mq, sp, stream);
+  // KVC_H2O_POLY=1: 4 of every 16 pairs of exponentials on the FMA pipe instead of MUFU (tc_helpers.cuh).  Measured
+  // SLOWER (L = 16384, B = 2: 11.26 ms with 0 of 16, 11.61 with 2, 12.7 with 4, 13.1 with 6): the loop is bound by
+  // instruction issue (ncu: issue 67 %, XU 68 %, ALU 61 %), and a polynomial exp2 costs 5.5 issue slots against 1.
+  static const bool poly = [] { const char* e = getenv("KVC_H2O_POLY"); return e && atoi(e) > 0; }();
+  if (poly) return dtype == KVC_BF16 ? launch<Bf16, 4>(mk, mq, sp, stream) : launch<Fp16, 4>(mk, mq, sp, stream);
+  return dtype == KVC_BF16 ? launch<Bf16, 0>(mk, mq, sp, stream) : launch<Fp16, 0>(mk, mq, sp, stream);
 }
 
 }  // namespace kvc
