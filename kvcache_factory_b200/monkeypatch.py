@@ -37,7 +37,8 @@ from . import pyramidkv_utils as U
 DENSE_METHODS = ("pyramidkv", "snapkv", "h2o", "streamingllm", "l2norm")
 FLAT_METHODS = ("adakv", "headkv")
 # methods of the reference that lie outside the hot path rebuilt here ("out of scope")
-UNSUPPORTED = ("cam", "minference", "think")
+THINK_METHODS = ("think",)
+UNSUPPORTED = ("cam", "minference")
 
 _ORIGINAL: Dict[type, Callable] = {}
 
@@ -54,6 +55,8 @@ def _init_cluster(module, method: str) -> None:
         U.init_StreamingLLM(module)
     elif method == "l2norm":
         U.init_l2norm(module)
+    elif method == "think":
+        U.init_think(module)
     elif method == "adakv":
         U.init_adakv(module)
     elif method == "headkv":
@@ -255,16 +258,86 @@ def _make_flat_forward(method: str, family):
     return forward
 
 
+def _make_think_forward(method: str, family):
+    """ThinK (``llama_attn_forward_think``, ``llama_model_think.py:120-216``; cache ``cache_utils_think.py:390-424``):
+    the prefill stores the channel-pruned keys, the kept-channel mask, the unpruned recent keys and the compressed values;
+    a decode step scores the pruned keys with the query's kept channels and the recent + new keys with the whole query."""
+    apply_rotary_pos_emb = family.apply_rotary_pos_emb
+    eager_attention_forward = family.eager_attention_forward
+    functions = family.ALL_ATTENTION_FUNCTIONS
+    repeat_kv = family.repeat_kv
+
+    def forward(self, hidden_states, position_embeddings=None, attention_mask=None, past_key_values=None, **kwargs):
+        input_shape = hidden_states.shape[:-1]
+        hidden_shape = (*input_shape, -1, self.head_dim)
+        query_states = self.q_proj(hidden_states).view(hidden_shape).transpose(1, 2)
+        key_states = self.k_proj(hidden_states).view(hidden_shape).transpose(1, 2)
+        value_states = self.v_proj(hidden_states).view(hidden_shape).transpose(1, 2)
+        cos, sin = position_embeddings
+        query_states, key_states = apply_rotary_pos_emb(query_states, key_states, cos, sin)
+        bsz, num_heads, q_len, d = query_states.shape
+        if past_key_values is None:
+            raise ValueError("think needs use_cache=True: its decode path reads the pruned key cache")
+        side = past_key_values.__dict__.setdefault("_kvc_think", {})
+        if _layer_keys(past_key_values, self.layer_idx) is None:      # ---- prefill ----
+            _init_cluster(self, method)
+            if self.kv_cluster.recent_size <= 0:
+                raise ValueError("think: recent_size must be positive (the unpruned recent keys mark the layer as prefilled)")
+            self.kv_seq_len = q_len
+            interface = functions.get_interface(self.config._attn_implementation, eager_attention_forward)
+            attn_output, attn_weights = interface(self, query_states, key_states, value_states, attention_mask,
+                                                  dropout=0.0 if not self.training else self.attention_dropout,
+                                                  scaling=self.scaling, **kwargs)
+            res = self.kv_cluster.update_think(key_states, query_states, value_states, attention_mask,
+                                               self.num_key_value_groups)
+            if len(res) == 2:                                         # below the capacity: nothing pruned (:357-358)
+                side[self.layer_idx] = None
+                past_key_values.update(repeat_kv(res[0], num_heads // res[0].shape[1]),
+                                       repeat_kv(res[1], num_heads // res[1].shape[1]), self.layer_idx)
+            else:
+                kv_pruned, kv_recent, mask, vc = res
+                side[self.layer_idx] = (kv_pruned.view(bsz, num_heads, -1, kv_pruned.shape[-1]), mask)
+                _store_prefill(past_key_values, kv_recent, vc, self.layer_idx, False)   # keys: recent rows, values: all
+            return self.o_proj(attn_output.reshape(*input_shape, -1).contiguous()), attn_weights
+        # ---- decode (llama_model_think.py:176-199) ----
+        if q_len != 1:
+            raise NotImplementedError("think: the pruned-key attention of the reference is defined for one query token")
+        self.kv_seq_len = getattr(self, "kv_seq_len", 0) + q_len
+        key_states = repeat_kv(key_states, self.num_key_value_groups)
+        value_states = repeat_kv(value_states, self.num_key_value_groups)
+        layer = past_key_values.layers[self.layer_idx]
+        if type(layer).__name__ == "DynamicLayer":                    # keys and values have different lengths here
+            layer.keys = torch.cat([layer.keys, key_states], dim=-2)
+            layer.values = torch.cat([layer.values, value_states], dim=-2)
+            k_recent, v_all = layer.keys, layer.values
+        else:
+            k_recent, v_all = past_key_values.update(key_states, value_states, self.layer_idx)
+        scale = d ** -0.5
+        w2 = torch.matmul(query_states, k_recent.transpose(2, 3)) * scale
+        state = side.get(self.layer_idx)
+        if state is not None:
+            key_pruned, mask = state
+            mq = query_states[mask.unsqueeze(2).expand(-1, -1, q_len, -1)].view(bsz, num_heads, q_len, -1)
+            w1 = torch.matmul(mq, key_pruned.transpose(2, 3)) * scale
+            w2 = torch.cat([w1, w2], dim=-1)
+        probs = torch.softmax(w2, dim=-1, dtype=torch.float32).to(query_states.dtype)
+        attn_output = torch.matmul(probs, v_all).transpose(1, 2)
+        return self.o_proj(attn_output.reshape(*input_shape, -1).contiguous()), None
+
+    forward.__name__ = "kvc_think_attention_forward"
+    return forward
+
+
 def _replace(method: str, family, attention_cls) -> None:
     if method == "fullkv":
         return
     if method in UNSUPPORTED:
         raise NotImplementedError(f"method '{method}' is outside the compression hot path rebuilt here "
-                                  f"(supported: {', '.join(DENSE_METHODS + FLAT_METHODS)}, fullkv)")
-    if method not in DENSE_METHODS + FLAT_METHODS:
+                                  f"(supported: {', '.join(DENSE_METHODS + FLAT_METHODS + THINK_METHODS)}, fullkv)")
+    if method not in DENSE_METHODS + FLAT_METHODS + THINK_METHODS:
         raise ValueError(f"unknown method '{method}'")
     _ORIGINAL.setdefault(attention_cls, attention_cls.forward)
-    maker = _make_forward if method in DENSE_METHODS else _make_flat_forward
+    maker = _make_forward if method in DENSE_METHODS else (_make_think_forward if method in THINK_METHODS else _make_flat_forward)
     attention_cls.forward = maker(method, family)
 
 

@@ -49,7 +49,7 @@ def test_method_strings_and_restore():
     import transformers.models.llama.modeling_llama as L
     import transformers.models.mistral.modeling_mistral as M
     orig_l, orig_m = L.LlamaAttention.forward, M.MistralAttention.forward
-    for m in ("pyramidkv", "snapkv", "h2o", "streamingllm", "l2norm", "adakv", "headkv"):
+    for m in ("pyramidkv", "snapkv", "h2o", "streamingllm", "l2norm", "think", "adakv", "headkv"):
         kvc.replace_llama(m)
         assert L.LlamaAttention.forward is not orig_l and m in L.LlamaAttention.forward.__name__
         kvc.replace_mistral(m)
@@ -59,7 +59,7 @@ def test_method_strings_and_restore():
     assert L.LlamaAttention.forward is orig_l and M.MistralAttention.forward is orig_m
     kvc.replace_llama("fullkv")
     assert L.LlamaAttention.forward is orig_l
-    for m in ("cam", "think", "minference"):
+    for m in ("cam", "minference"):
         with pytest.raises(NotImplementedError):
             kvc.replace_llama(m)
     with pytest.raises(ValueError):
@@ -111,6 +111,76 @@ def test_compressed_cache_flow_on_cpu(monkeypatch):
         assert torch.allclose(a, b, atol=1e-5)
 
 
+class OracleThink:
+    """SnapKVCluster stand-in for the ThinK hook: ``update_think`` on the CPU restatement; ``update_kv`` returns the same
+    compressed cache with the dropped channels of the non-recent rows ZEROED -- q.k over the kept channels equals q.k_zeroed,
+    so the plain compressed-cache hook on this cluster must reproduce the ThinK hook's logits."""
+
+    knobs = (32, 0.4)     # init_snapkv does not pass ThinK's two knobs: the test sets them here for the zeroed-cache run
+
+    def __init__(self, window_size=64, max_capacity_prompt=320, kernel_size=5, pooling="avgpool", merge=None,
+                 recent_size=None, ratio=None):
+        recent_size = OracleThink.knobs[0] if recent_size is None else recent_size
+        ratio = OracleThink.knobs[1] if ratio is None else ratio
+        self.kw = dict(window_size=window_size, max_capacity_prompt=max_capacity_prompt, kernel_size=kernel_size,
+                       pooling=pooling, recent_size=recent_size, ratio=ratio)
+        self.recent_size, self.ratio = recent_size, ratio
+
+    def update_think(self, key_states, query_states, value_states, attention_mask, num_key_value_groups):
+        res = O.think_update_kv(key_states, query_states, value_states, **self.kw)
+        return res if len(res) == 2 else res[:4]
+
+    def update_kv(self, key_states, query_states, value_states, attention_mask, num_key_value_groups):
+        res = O.think_update_kv(key_states, query_states, value_states, **self.kw)
+        if len(res) == 2:
+            return res
+        _, _, mask, vc, kc, _ = res
+        kz = kc.clone()
+        rows = kc.shape[2] - self.recent_size
+        kz[:, :, :rows, :] = kz[:, :, :rows, :] * mask.unsqueeze(2).to(kz.dtype)
+        return kz, vc
+
+
+@pytest.mark.parametrize("ratio", [0.07, 0.4])
+def test_think_hook_equals_zeroed_channel_cache_on_cpu(monkeypatch, ratio):
+    """ThinK through the hooks: pruned keys + kept-channel mask + recent keys + all values in the cache; decode logits equal
+    the ordinary compressed-cache hook on a cache whose dropped channels are zero."""
+    monkeypatch.setattr(U, "SnapKVCluster", OracleThink)
+    monkeypatch.setattr(OracleThink, "knobs", (6, ratio))
+    L, new = 60, 5
+    ids = torch.randint(0, 97, (1, L), generator=torch.Generator().manual_seed(4))
+    outs = {}
+    for method in ("think", "snapkv"):
+        MP.restore()
+        model = tiny()
+        kvc.replace_llama(method)
+        c = model.config
+        c.max_capacity_prompt, c.window_size, c.kernel_size, c.pooling, c.merge = 24, 8, 5, "avgpool", None
+        c.recent_size, c.ratio = 6, ratio
+        outs[method] = model.generate(ids, max_new_tokens=new, do_sample=False, use_cache=True,
+                                      return_dict_in_generate=True, output_logits=True)
+    MP.restore()
+    cache = outs["think"].past_key_values
+    side = cache.__dict__["_kvc_think"]
+    d, k = 16, int(16 * ratio)
+    assert side[0][0].shape == (1, 4, 24 - 6, d - k) and side[0][1].shape == (1, 4, d) and side[0][1].dtype == torch.bool
+    assert cache.layers[0].keys.shape == (1, 4, 6 + new - 1, d) and cache.layers[0].values.shape == (1, 4, 24 + new - 1, d)
+    assert torch.equal(outs["think"].sequences, outs["snapkv"].sequences)
+    for a, b in zip(outs["think"].logits, outs["snapkv"].logits):
+        assert torch.allclose(a, b, atol=2e-5), float((a - b).abs().max())
+
+
+def test_think_hook_passthrough_below_capacity():
+    model = tiny()
+    ids = torch.randint(0, 97, (1, 40), generator=torch.Generator().manual_seed(1))
+    ref = model.generate(ids, max_new_tokens=6, do_sample=False, use_cache=True)
+    kvc.replace_llama("think")
+    model.config.max_capacity_prompt, model.config.window_size = 64, 8
+    out = model.generate(ids, max_new_tokens=6, do_sample=False, use_cache=True)
+    MP.restore()
+    assert torch.equal(out, ref)
+
+
 @pytest.mark.gpu
 def test_snapkv_hook_runs_cuda_path_in_a_tiny_llama():
     dev = torch.device("cuda:0")
@@ -149,6 +219,51 @@ def test_snapkv_hook_runs_cuda_path_in_a_tiny_llama():
     cache = out.past_key_values
     assert cache.layers[0].keys.shape == (1, 4, cap + new - 1, 128)
     assert out.sequences.shape == (1, L + new)
+
+
+@pytest.mark.gpu
+def test_think_hook_runs_cuda_path_in_a_tiny_llama(monkeypatch):
+    """replace_llama("think") on the GPU: kvc_think_prune feeds the cache; decode logits agree with the plain
+    compressed-cache hook run on the same CUDA cluster with the dropped channels zeroed."""
+    dev = torch.device("cuda:0")
+    w, cap, ks, recent, ratio = 32, 128, 7, 16, 0.4
+
+    class ZeroedSnap(U.SnapKVCluster):
+        def update_kv(self, key_states, query_states, value_states, attention_mask, groups, **kw):
+            kc, vc = super().update_kv(key_states, query_states, value_states, attention_mask, groups)
+            if kc.shape[2] != cap:
+                return kc, vc
+            _, _, mask = kvc._native.think_prune(kc, query_states, recent, ratio)
+            kz = kc.clone()
+            kz[:, :, :cap - recent] = kz[:, :, :cap - recent] * mask.unsqueeze(2).to(kz.dtype)
+            return kz, vc
+
+    L, new = 700, 4
+    ids = torch.randint(0, 97, (1, L), generator=torch.Generator().manual_seed(3)).to(dev)
+    outs = {}
+    for method in ("think", "snapkv"):
+        MP.restore()
+        if method == "snapkv":
+            monkeypatch.setattr(U, "SnapKVCluster", ZeroedSnap)
+        model = tiny(dtype=torch.bfloat16, head_dim=128).to(dev)
+        kvc.replace_llama(method)
+        c = model.config
+        c.max_capacity_prompt, c.window_size, c.kernel_size, c.pooling, c.merge = cap, w, ks, "avgpool", None
+        c.recent_size, c.ratio = recent, ratio
+        outs[method] = model.generate(ids, max_new_tokens=new, do_sample=False, use_cache=True,
+                                      return_dict_in_generate=True, output_logits=True)
+    MP.restore()
+    torch.cuda.synchronize()
+    cache = outs["think"].past_key_values
+    pruned, mask = cache.__dict__["_kvc_think"][0]
+    k = int(128 * ratio)
+    assert pruned.shape == (1, 4, cap - recent, 128 - k) and pruned.is_cuda and mask.dtype == torch.bool
+    assert bool((mask.sum(-1) == 128 - k).all())
+    assert cache.layers[0].keys.shape == (1, 4, recent + new - 1, 128)
+    assert cache.layers[0].values.shape == (1, 4, cap + new - 1, 128)
+    for a, b in zip(outs["think"].logits, outs["snapkv"].logits):
+        assert bool(torch.isfinite(a).all())
+        assert float((a.float() - b.float()).abs().max()) <= 0.05 * float(b.float().abs().max()) + 1e-3
 
 
 @pytest.mark.gpu
