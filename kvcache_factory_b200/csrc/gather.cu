@@ -1,6 +1,8 @@
 // Row movers: dense/varlen gather-compact of the selected K,V rows and the flattened-cache append.
 // Pure HBM traffic: every row is moved as 16-byte vectors (a d=128 bf16 row is 256 B = 16 lanes),
 // several rows in flight per thread, streaming (no-L1-allocate) loads and stores.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace kvc {
@@ -21,6 +23,7 @@ gather_rows_kernel(RowSrc ksrc, RowSrc vsrc, const int32_t* __restrict__ idx, in
                    const int32_t* __restrict__ cap, const int32_t* __restrict__ cu_klen,
                    int Hq, int groups, int L, int w, int n_sel, int chunks_per_row,
                    char* __restrict__ out_k, char* __restrict__ out_v, unsigned long long* tl) {
+  asm volatile("griddepcontrol.wait;" ::: "memory");   // programmatic dependent launch (KVC_PDL_TAIL): see gather_dense
   tl_start(tl);
   const int unit = blockIdx.y;
   const int b = unit / Hq, h = unit % Hq;
@@ -95,6 +98,22 @@ int gather_dense(const void* k, int64_t k_sb, int64_t k_sh, int64_t k_sl, const 
   const int block_rows = (kGatherThreads / cpr) * kGatherUnroll;
   dim3 grid((rows + block_rows - 1) / block_rows, B * Hq);
   RowSrc ks{(const char*)k, k_sb * e, k_sh * e, k_sl * e}, vs{(const char*)v, v_sb * e, v_sh * e, v_sl * e};
+  static const bool pdl = [] { const char* e = getenv("KVC_PDL_TAIL"); return e && atoi(e) == 1; }();
+  if (pdl) {   // let the grid be scheduled while the select that produces the indices is still draining
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kGatherThreads);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const int32_t* nocap = nullptr;
+    KVC_CUDA_TRY(cudaLaunchKernelEx(&cfg, gather_rows_kernel<false>, ks, vs, idx, (int64_t)n_sel, nocap, nocap, Hq, Hq / Hkv, L, w,
+                                    n_sel, cpr, (char*)out_k, (char*)out_v, KVC_TL_SLOT(2)));
+    return launch_status("gather_rows_kernel<dense>");
+  }
   gather_rows_kernel<false><<<grid, kGatherThreads, 0, stream>>>(ks, vs, idx, n_sel, nullptr, nullptr, Hq, Hq / Hkv,
                                                                   L, w, n_sel, cpr, (char*)out_k, (char*)out_v, KVC_TL_SLOT(2));
   return launch_status("gather_rows_kernel<dense>");

@@ -198,6 +198,9 @@ __global__ void __launch_bounds__(kThreads, kThreads == 512 ? 2 : 1)
 topk_cluster_kernel(const uint16_t* __restrict__ scores, int n, int kernel_size, int k_fixed,
                     const int32_t* __restrict__ k_per_row, int32_t* __restrict__ out_idx, int64_t idx_stride,
                     uint16_t* __restrict__ out_pooled, float* __restrict__ out_sums, unsigned long long* tl) {
+  // programmatic dependent launch (KVC_PDL_TAIL): the grid may be scheduled while the kernel that produces the scores
+  // is still draining; nothing is read before this point
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   tl_start(tl);
   constexpr int SL = kThreads * E;          // slice length
   constexpr int kWarps = kThreads / 32;
@@ -565,8 +568,13 @@ static int launch(const void* scores, int rows, int n, int C, int kernel_size, i
   attr[0].val.clusterDim.x = C;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cudaLaunchAttribute attr2[2];
+  static const bool pdl = [] { const char* e = getenv("KVC_PDL_TAIL"); return e && atoi(e) == 1; }();
+  attr2[0] = attr[0];
+  attr2[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr2[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = pdl ? attr2 : attr;
+  cfg.numAttrs = pdl ? 2 : 1;
   const uint16_t* sc = (const uint16_t*)scores;
   uint16_t* op = (uint16_t*)out_pooled;
   unsigned long long* tl = KVC_TL_SLOT(1);
