@@ -404,7 +404,9 @@ int kvc_adakv_prefill(const void* q, int64_t q_sh, int64_t q_sl, const void* k, 
   if (int rc = kvc_adakv_allocate(ws + a.pooled, sums, Hq, n, dtype, base_capacity, one_minus_floor, floor_capacity, normalize, w,
                                   out_cap, out_head_lens, out_cu_klen, ws + a.ws_alloc, a.al_ws, stream))
     return rc;
-  // the reference reads the capacities back here as well (:718); everything after it is sized by them
+  // the reference reads the capacities back here as well (:718); everything after it is sized by them.  (Queuing the
+  // per-head select and the gather BEFORE the read, on the device-side capacities with 8192-wide index rows, was measured
+  // twice -- from Python and from this function -- and is slower: 254 vs 226 us per cfg-4 layer.)
   KVC_CUDA_TRY(cudaMemcpyAsync(host_cap, out_cap, (size_t)Hq * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   KVC_CUDA_TRY(cudaStreamSynchronize(st));
   int max_cap = 0;
