@@ -1,4 +1,4 @@
-import sys; sys.path.insert(0, "/root/repo")
+import os, sys; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from kvcache_factory_b200 import PyramidKVCluster, wait_for_compression, _native
 dev = torch.device("cuda:0"); L, w, cap, nl = 32768, 32, 2048, 32
