@@ -591,7 +591,8 @@ static int dispatch_e(const void* scores, int rows, int n, int kernel_size, int 
   // 512-thread variant: 64 registers and ~67 KB of shared memory, so TWO CTAs fit on an SM and the selects of
   // consecutive layers (issued on rotating side streams by the host mirror) overlap their latency chains:
   // 10.4 us per layer for two overlapped selects against 15.8 us back to back with the 1024-thread variant,
-  // 16.5 us when alone.  With 3 CTAs per SM (40 registers) the spills cost more than the overlap gains.
+  // 16.5 us when alone.  With 3 CTAs per SM (40 registers) the spills cost more than the overlap gains; 8-CTA clusters of
+  // 512 x 8 (two CTAs of ONE launch per SM) are slower as well: 17.1 vs 13.5 us alone, 12.4 vs 9.2 us in pairs (round 2).
   // KVC_SELECT_THREADS=1024 forces the one-CTA-per-SM variant.
   static const bool half = [] { const char* e = getenv("KVC_SELECT_THREADS"); return !(e && atoi(e) == 1024); }();
   // (for longer rows the 8- and 16-CTA clusters of this variant were measured slower than 1024 x 16: 77 vs 69 us
